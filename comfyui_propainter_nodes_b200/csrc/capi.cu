@@ -1,0 +1,177 @@
+// extern "C" surface of libpropainter_b200.so (declared in include/propainter_b200.h).
+#include <string.h>
+
+#include "../../include/propainter_b200.h"
+#include "engine.cuh"
+
+#define PP_HANDLE(h)                                     \
+  if ((h) == nullptr) {                                  \
+    pp_set_error("null engine handle");                  \
+    return PP_ERR_ARG;                                   \
+  }                                                      \
+  PPEngine& e = *reinterpret_cast<PPEngine*>(h);         \
+  if (cudaSetDevice(e.device) != cudaSuccess) {          \
+    pp_set_error("cudaSetDevice(%d) failed", e.device);  \
+    return PP_ERR_CUDA;                                  \
+  }
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* pp_version(void) { return "propainter_b200 1 sm_100a"; }
+
+int pp_create(int device, void* workspace, size_t workspace_bytes, pp_handle* out) {
+  PP_REQUIRE(out != nullptr, "pp_create: out is null");
+  PP_REQUIRE(workspace != nullptr && workspace_bytes >= (64u << 20), "pp_create: workspace must be >= 64 MiB");
+  PP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_create: workspace must be 256-byte aligned");
+  PP_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PP_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  PP_REQUIRE(prop.major == 10, "pp_create: this library is built for sm_100a (Blackwell B200); device %d is sm_%d%d",
+             device, prop.major, prop.minor);
+  PPEngine* e = new PPEngine();
+  e->device = device;
+  e->arena.base = static_cast<uint8_t*>(workspace);
+  e->arena.cap = workspace_bytes;
+  *out = reinterpret_cast<pp_handle>(e);
+  return PP_OK;
+}
+
+int pp_destroy(pp_handle h) {
+  if (h != nullptr) delete reinterpret_cast<PPEngine*>(h);
+  return PP_OK;
+}
+
+int pp_register_conv(pp_handle h, const char* name, const void* w, const float* bias, int cout_g, int cout_g_pad,
+                     int bn, int cin_g, int kh, int kw, int groups) {
+  PP_HANDLE(h);
+  PP_REQUIRE(name != nullptr && w != nullptr, "pp_register_conv: null argument");
+  PP_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256 && cout_g_pad % bn == 0 && cout_g <= cout_g_pad && cin_g % 8 == 0,
+             "pp_register_conv(%s): invalid packing (cout_g=%d pad=%d bn=%d cin_g=%d)", name, cout_g, cout_g_pad, bn,
+             cin_g);
+  PPPackedConv c;
+  c.w = static_cast<const __half*>(w); c.b = bias;
+  c.cout_g = cout_g; c.cout_g_pad = cout_g_pad; c.bn = bn; c.cin_g = cin_g; c.kh = kh; c.kw = kw; c.groups = groups;
+  e.convs[name] = c;
+  return PP_OK;
+}
+
+int pp_register_tensor(pp_handle h, const char* name, const void* ptr, size_t bytes) {
+  PP_HANDLE(h);
+  PP_REQUIRE(name != nullptr && ptr != nullptr, "pp_register_tensor: null argument");
+  PPTensor t;
+  t.ptr = ptr; t.bytes = bytes;
+  e.tensors[name] = t;
+  return PP_OK;
+}
+
+int pp_raft_bidir(pp_handle h, const float* frames, int T, int H, int W, int iters, float* flows_f, float* flows_b,
+                  void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(frames && flows_f && flows_b, "pp_raft_bidir: null pointer");
+  return pp_stage_raft(e, frames, T, H, W, iters, flows_f, flows_b, as_stream(stream));
+}
+
+int pp_flow_complete(pp_handle h, const float* flows_f, const float* flows_b, const float* flow_masks, int T, int H,
+                     int W, float* out_f, float* out_b, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(flows_f && flows_b && flow_masks && out_f && out_b, "pp_flow_complete: null pointer");
+  return pp_stage_flow_complete(e, flows_f, flows_b, flow_masks, T, H, W, out_f, out_b, as_stream(stream));
+}
+
+int pp_image_propagate(pp_handle h, const float* frames, const float* masks, const float* flows_f,
+                       const float* flows_b, int T, int H, int W, float* updated_frames, float* updated_masks,
+                       void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(frames && masks && flows_f && flows_b && updated_frames && updated_masks,
+             "pp_image_propagate: null pointer");
+  return pp_stage_image_propagate(e, frames, masks, flows_f, flows_b, T, H, W, updated_frames, updated_masks,
+                                  as_stream(stream));
+}
+
+int pp_gen_begin(pp_handle h, const float* updated_frames, const float* masks_dilated, const float* updated_masks,
+                 const float* flows_f, const float* flows_b, int T, int H, int W, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(updated_frames && masks_dilated && updated_masks && flows_f && flows_b, "pp_gen_begin: null pointer");
+  return pp_stage_gen_begin(e, updated_frames, masks_dilated, updated_masks, flows_f, flows_b, T, H, W, as_stream(stream));
+}
+
+int pp_gen_window(pp_handle h, const int* frame_ids, int t, int l_t, void* pred_f16, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(frame_ids && pred_f16, "pp_gen_window: null pointer");
+  return pp_stage_gen_window(e, frame_ids, t, l_t, static_cast<__half*>(pred_f16), as_stream(stream));
+}
+
+int pp_gen_end(pp_handle h) {
+  PP_HANDLE(h);
+  return pp_stage_gen_end(e);
+}
+
+int pp_composite(pp_handle h, const void* pred_f16, const float* masks_dilated, const uint8_t* orig, uint8_t* comp,
+                 const int* frame_ids_dev, const int* first_visit_dev, int l_t, int H, int W, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(pred_f16 && masks_dilated && orig && comp && frame_ids_dev && first_visit_dev, "pp_composite: null pointer");
+  e.launches++;
+  return pp_k_composite(static_cast<const __half*>(pred_f16), 4, masks_dilated, orig, comp, frame_ids_dev,
+                        first_visit_dev, l_t, H, W, as_stream(stream));
+}
+
+long long pp_launch_count(pp_handle h) { return h ? reinterpret_cast<PPEngine*>(h)->launches : 0; }
+size_t pp_workspace_peak(pp_handle h) { return h ? reinterpret_cast<PPEngine*>(h)->arena.peak : 0; }
+
+// ---- single-operator entry points --------------------------------------------------------------------
+int pp_op_conv(pp_handle h, const char* name, const void* x_f16, int N, int H, int W, int stride, int pad, int dil,
+               int replicate, int act, float slope, const void* residual_f16, void* out_f16, void* stream) {
+  PP_HANDLE(h);
+  const PPPackedConv* w = nullptr;
+  PP_TRY(pp_get_conv(e, name, &w));
+  PPConvCall c(e, name, N, H, W);
+  c.in(static_cast<const __half*>(x_f16), w->cin_g * w->groups, 0, w->cin_g, w->groups > 1 ? w->cin_g : 0)
+      .geom(stride, stride, pad, pad, dil, dil, replicate)
+      .out(out_f16, w->cout_g * w->groups, 0, 0, w->groups > 1 ? w->cout_g : 0)
+      .act(act, slope);
+  if (residual_f16 != nullptr) c.residual(static_cast<const __half*>(residual_f16), w->cout_g * w->groups, 0);
+  return c.run(as_stream(stream));
+}
+
+int pp_op_corr_lookup(pp_handle h, const void* l0, const void* l1, const void* l2, const void* l3,
+                      const float* coords, void* out_f16, long long nq, int h8, int w8, void* stream) {
+  PP_HANDLE(h);
+  e.launches++;
+  return pp_k_corr_lookup(static_cast<const __half*>(l0), static_cast<const __half*>(l1),
+                          static_cast<const __half*>(l2), static_cast<const __half*>(l3), coords,
+                          static_cast<__half*>(out_f16), 328, nq, h8 * w8, h8, w8, as_stream(stream));
+}
+
+int pp_op_imgprop_step(pp_handle h, const void* cur4_f16, const void* prop_in4_f16, void* prop_out4_f16,
+                       const void* flow_prop_f16, const void* flow_check_f16, int H, int W, void* stream) {
+  PP_HANDLE(h);
+  e.launches++;
+  return pp_k_imgprop_step(static_cast<const __half*>(cur4_f16), static_cast<const __half*>(prop_in4_f16),
+                           static_cast<__half*>(prop_out4_f16), static_cast<const __half*>(flow_prop_f16),
+                           static_cast<const __half*>(flow_check_f16), H, W, as_stream(stream));
+}
+
+int pp_op_attention(pp_handle h, const void* qkv_f16, const void* pkv_f16, void* out_f16, const int* win_flags_dev,
+                    int t, int gh, int gw, int n_pool, int parity, void* stream) {
+  PP_HANDLE(h);
+  const int nh = pp_ceil_div(gh, 5) * 5, nw = pp_ceil_div(gw, 9) * 9;
+  std::vector<int> ring;
+  pp_build_ring_indices(nh, nw, ring);
+  const size_t mark = e.arena.mark();
+  int* ring_dev;
+  PP_TRY(pp_alloc(e, &ring_dev, ring.size(), "ring indices"));
+  PP_CUDA_CHECK(cudaMemcpyAsync(ring_dev, ring.data(), ring.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                as_stream(stream)));
+  const __half* qkv = static_cast<const __half*>(qkv_f16);
+  const __half* pkv = static_cast<const __half*>(pkv_f16);
+  int r = pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, static_cast<__half*>(out_f16), 512,
+                         win_flags_dev, ring_dev, t, gh, gw, nh, nw, n_pool, parity, as_stream(stream));
+  PP_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+  e.arena.release(mark);
+  e.launches++;
+  return r;
+}
+
+}  // extern "C"

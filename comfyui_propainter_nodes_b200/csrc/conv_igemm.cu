@@ -1,0 +1,298 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.  See conv_igemm.cuh for the contract.
+//
+// CTA = 192 threads, one 128 x BN output tile:
+//   warps 0-3  im2col producers: 16-byte cp.async gathers into a 128B-swizzled K-major A tile,
+//              then the epilogue (TMEM -> registers -> bias/activation/fusions -> global)
+//   warp  4    one elected lane issues tcgen05.mma (M=128, N=BN, K=16 x4 per 64-wide K chunk)
+//   warp  5    TMEM allocation; one lane streams the pre-swizzled weight tile with a single
+//              cp.async.bulk (TMA engine) per stage
+// Pipeline: `stages` smem slots, full/empty mbarriers; the accumulator (128 lanes x BN fp32 columns)
+// lives in tensor memory until the epilogue.
+#include "conv_igemm.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int NUM_PRODUCERS = 128;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 100 * 1024;
+
+__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+  switch (act) {
+    case PP_ACT_RELU: return fmaxf(v, 0.f);
+    case PP_ACT_LRELU: return v > 0.f ? v : v * slope;
+    case PP_ACT_SIGMOID: return ppx::sigmoidf_(v);
+    case PP_ACT_TANH: return tanhf(v);
+    case PP_ACT_GELU: return ppx::gelu_erf(v);
+    default: return v;
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_constant__ PPConvParams p) {
+  using namespace ppx;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int S = p.stages;
+  const int b_stage_bytes = p.BN * 128;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* accum_bar = empty_bar + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int g = blockIdx.z;
+  const int num_kc = p.num_kc;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], NUM_PRODUCERS + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ im2col producers
+    const int j = tid & 7;    // 16-byte chunk inside the 128-byte K row
+    const int rb = tid >> 3;  // rows rb, rb+16, ..., rb+112
+    int rpix[8], riy[8], rix[8];
+    uint32_t rvalid = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + rb + 16 * i;
+      if (m < p.M_total) {
+        const int ox = m % p.OW;
+        const int t = m / p.OW;
+        const int oy = t % p.OH;
+        const int img = t / p.OH;
+        rpix[i] = img * p.H * p.W;
+        riy[i] = oy * p.sh - p.ph;
+        rix[i] = ox * p.sw - p.pw;
+        rvalid |= 1u << i;
+      } else {
+        rpix[i] = 0; riy[i] = 0; rix[i] = 0;
+      }
+    }
+    const uint32_t a_off = rb * 128 + ((j ^ (rb & 7)) << 4);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int kc = 0; kc < num_kc; ++kc) {
+      mbar_wait(&empty_bar[s], phase ^ 1);
+      const int k = kc * BK + j * 8;
+      const bool kvalid = k < p.K_total;
+      const int tap = k / p.Cin;
+      const int ci = k - tap * p.Cin;
+      const int ky = tap / p.kw;
+      const int kx = tap - ky * p.kw;
+      int q = 0;
+#pragma unroll
+      for (int t = 1; t < 4; ++t)
+        if (t < p.nseg && ci >= p.seg[t].cbegin) q = t;
+      const __half* sbase = p.seg[q].ptr + p.seg[q].coff + g * p.seg[q].gstep + (ci - p.seg[q].cbegin);
+      const long long cs = p.seg[q].cstride;
+      const int dy = ky * p.dh, dx = kx * p.dw;
+      const uint32_t a_dst = smem_u32(smem + s * stage_bytes) + a_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int iy = riy[i] + dy, ix = rix[i] + dx;
+        bool v = kvalid && ((rvalid >> i) & 1u);
+        if (p.pad_replicate) {
+          iy = min(max(iy, 0), p.H - 1);
+          ix = min(max(ix, 0), p.W - 1);
+        } else {
+          v = v && ((unsigned)iy < (unsigned)p.H) && ((unsigned)ix < (unsigned)p.W);
+        }
+        const __half* src = v ? sbase + (long long)(rpix[i] + iy * p.W + ix) * cs : p.seg[0].ptr;
+        cp_async16(a_dst + i * (16 * 128), src, v ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (kc >= 2) {
+        cp_async_wait<2>();
+        fence_proxy_async();
+        int sp = s - 2; if (sp < 0) sp += S;
+        mbar_arrive(&full_bar[sp]);
+      }
+      if (++s == S) { s = 0; phase ^= 1; }
+    }
+    if (num_kc >= 2) {
+      cp_async_wait<1>();
+      fence_proxy_async();
+      mbar_arrive(&full_bar[(num_kc - 2) % S]);
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    mbar_arrive(&full_bar[(num_kc - 1) % S]);
+
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    const bool mvalid = m < p.M_total;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const long long mrow = m;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t raw[16];
+      tmem_ld16(t_row + c0, raw);
+      tmem_ld_wait();
+      const int ng0 = n0 + c0;  // channel within the group
+      if (!mvalid || ng0 >= p.Cout_g) continue;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int ng = ng0 + i;
+        float x = __uint_as_float(raw[i]);
+        if (p.bias != nullptr && ng < p.Cout_g) x += __ldg(p.bias + g * p.Cout_g + ng);
+        v[i] = x;
+      }
+      const int nvalid = min(16, p.Cout_g - ng0);
+      if (p.epi == PP_EPI_STD) {
+        const __half* res = p.aux0 ? p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0 : nullptr;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = act_apply(v[i], p.act1, p.slope) * p.scale;
+          if (res != nullptr && i < nvalid) x += __half2float(res[i]);
+          v[i] = act_apply(x, p.act2, p.slope);
+        }
+        const long long o = mrow * p.out_cstride + p.out_coff + (long long)g * p.out_gstep + ng0;
+        if (p.out_fp32) {
+          float* dst = reinterpret_cast<float*>(p.out) + o;
+          if (nvalid == 16 && ((o & 3) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+          }
+        } else {
+          __half* dst = reinterpret_cast<__half*>(p.out) + o;
+          if (nvalid == 16 && ((o & 7) == 0)) {
+            __align__(16) __half2 h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
+            reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
+          } else {
+            for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(v[i]);
+          }
+        }
+      } else if (p.epi == PP_EPI_GRU_ZR) {
+        const int half_c = p.Cout_g >> 1;
+        if (ng0 < half_c) {
+          __half* dst = reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0;
+          for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(ppx::sigmoidf_(v[i]));
+        } else {
+          const int c = ng0 - half_c;
+          const __half* h = p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c;
+          __half* dst = p.out2 + mrow * p.out2_cstride + p.out2_coff + c;
+          for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(ppx::sigmoidf_(v[i]) * __half2float(h[i]));
+        }
+      } else {  // PP_EPI_GRU_H
+        const __half* h = p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0;
+        const __half* z = p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0;
+        __half* dst = reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0;
+        for (int i = 0; i < nvalid; ++i) {
+          const float zz = __half2float(z[i]);
+          dst[i] = __float2half_rn((1.f - zz) * __half2float(h[i]) + zz * tanhf(v[i]));
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(BM, p.BN);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        fence_proxy_async();
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+        const uint64_t adesc = umma_desc_sw128_kmajor(a_addr);
+        const uint64_t bdesc = umma_desc_sw128_kmajor(a_addr + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (++s == S) { s = 0; phase ^= 1; }
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ weight-tile loader (TMA bulk copy)
+    if (lane == 0) {
+      const __half* wsrc = p.wpacked + ((long long)g * num_kc * p.Cout_g_pad + n0) * BK;
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
+        bulk_g2s(smem_u32(smem + s * stage_bytes + A_STAGE_BYTES), wsrc + (long long)kc * p.Cout_g_pad * BK,
+                 (uint32_t)b_stage_bytes, &full_bar[s]);
+        if (++s == S) { s = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
+  PPConvParams p = pin;
+  PP_REQUIRE(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "conv: BN=%d must be a multiple of 16 in [16,256]", p.BN);
+  PP_REQUIRE(p.Cout_g_pad % p.BN == 0, "conv: Cout_g_pad=%d not a multiple of BN=%d", p.Cout_g_pad, p.BN);
+  PP_REQUIRE(p.Cin % 8 == 0, "conv: Cin=%d must be a multiple of 8", p.Cin);
+  PP_REQUIRE(p.nseg >= 1 && p.nseg <= 4, "conv: nseg=%d", p.nseg);
+  PP_REQUIRE(p.seg[p.nseg - 1].cend == p.Cin && p.seg[0].cbegin == 0, "conv: segments do not cover Cin=%d", p.Cin);
+  for (int i = 0; i < p.nseg; ++i) {
+    PP_REQUIRE(p.seg[i].cstride % 8 == 0 && p.seg[i].coff % 8 == 0 && p.seg[i].gstep % 8 == 0 &&
+                   p.seg[i].cbegin % 8 == 0 && p.seg[i].cend % 8 == 0,
+               "conv: segment %d is not 16-byte aligned (cstride=%d coff=%d)", i, p.seg[i].cstride, p.seg[i].coff);
+    PP_REQUIRE((reinterpret_cast<uintptr_t>(p.seg[i].ptr) & 15) == 0, "conv: segment %d pointer misaligned", i);
+  }
+  PP_REQUIRE((reinterpret_cast<uintptr_t>(p.wpacked) & 15) == 0, "conv: weight pointer misaligned");
+  p.K_total = p.kh * p.kw * p.Cin;
+  p.num_kc = pp_ceil_div(p.K_total, BK);
+  p.M_total = p.N * p.OH * p.OW;
+  if (p.M_total <= 0) return PP_OK;
+  const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
+  int stages = SMEM_BUDGET / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 3) stages = 3;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(pp_ceil_div(p.M_total, BM), p.Cout_g_pad / p.BN, p.groups);
+  conv_igemm_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}

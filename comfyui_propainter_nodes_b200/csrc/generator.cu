@@ -1,0 +1,284 @@
+// Stage 3b: InpaintGenerator (reference: model/propainter.py:358-453, model/modules/sparse_transformer.py).
+//
+// Session API: pp_gen_begin() encodes every frame ONCE (the reference re-encodes a frame in every sliding
+// window it appears in; the encoder is per-frame, so caching is result-identical) and down-samples flows and
+// masks once; pp_gen_window() then runs feature propagation + transformer + decoder for one window given
+// frame indices into the session.
+#include <string.h>
+
+#include "engine.cuh"
+
+namespace {
+
+constexpr int WIN_H = 5, WIN_W = 9, RING = 193;
+
+// 45 own-window token indices followed by the 148 ring tokens of the four rolled copies, in the order of
+// valid_ind_rolled (sparse_transformer.py:182-197, 232-283).  Indices address the padded [nh][nw] grid.
+}  // namespace
+
+void pp_build_ring_indices(int nh, int nw, std::vector<int>& out) {
+  constexpr int WIN_H = 5, WIN_W = 9, RING = 193;
+  const int nwh = nh / WIN_H, nww = nw / WIN_W;
+  const int eh = (WIN_H + 1) / 2, ew = (WIN_W + 1) / 2;
+  out.assign((size_t)nwh * nww * RING, 0);
+  for (int wy = 0; wy < nwh; ++wy)
+    for (int wx = 0; wx < nww; ++wx) {
+      int* dst = &out[((size_t)wy * nww + wx) * RING];
+      int n = 0;
+      for (int iy = 0; iy < WIN_H; ++iy)
+        for (int ix = 0; ix < WIN_W; ++ix) dst[n++] = (wy * WIN_H + iy) * nw + wx * WIN_W + ix;
+      // rolled copies: torch.roll(k, shifts=(sy, sx)) => rolled[y][x] = k[(y - sy) mod nh][(x - sx) mod nw]
+      const int sy[4] = {-eh, -eh, eh, eh}, sx[4] = {-ew, ew, -ew, ew};
+      for (int r = 0; r < 4; ++r)
+        for (int iy = 0; iy < WIN_H; ++iy)
+          for (int ix = 0; ix < WIN_W; ++ix) {
+            const bool top = r < 2, left = (r % 2) == 0;
+            // corner masks: tl zero on [:-eh, :-ew]; tr zero on [:-eh, ew:]; bl zero on [eh:, :-ew]; br zero on [eh:, ew:]
+            const bool zy = top ? (iy < WIN_H - eh) : (iy >= eh);
+            const bool zx = left ? (ix < WIN_W - ew) : (ix >= ew);
+            if (zy && zx) continue;
+            const int y = ((wy * WIN_H + iy - sy[r]) % nh + nh) % nh;
+            const int x = ((wx * WIN_W + ix - sx[r]) % nw + nw) % nw;
+            dst[n++] = y * nw + x;
+          }
+    }
+}
+
+namespace {
+
+int deconv(PPEngine& e, const std::string& name, const __half* x, int n, int h, int w, int cin, __half* up,
+           __half* out, int cout, int out_cs, int act, float slope, cudaStream_t st) {
+  PP_TRY(pp_k_upsample2x(x, cin, 0, up, cin, 0, n, h, w, cin, st));
+  e.launches++;
+  return PPConvCall(e, name, n, 2 * h, 2 * w).in(up, cin, 0, cin).out(out, out_cs, 0).act(act, slope).run(st);
+}
+
+}  // namespace
+
+int pp_stage_gen_end(PPEngine& e) {
+  if (e.gen.active) {
+    e.arena.release(e.gen.arena_mark);
+    e.gen = PPEngine::GenSession();
+  }
+  return PP_OK;
+}
+
+int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, const float* masks_upd,
+                 const float* flows_f, const float* flows_b, int T, int H, int W, cudaStream_t st) {
+  PP_REQUIRE(H % 8 == 0 && W % 8 == 0, "generator: size %dx%d must be a multiple of 8", W, H);
+  pp_stage_gen_end(e);
+  PPEngine::GenSession& g = e.gen;
+  g.arena_mark = e.arena.mark();
+  g.active = true;
+  g.T = T; g.H = H; g.W = W;
+  const int h4 = H / 4, w4 = W / 4, h2 = H / 2, w2 = W / 2;
+  const long long P4 = (long long)h4 * w4;
+  g.gh = (h4 + 2 * 3 - 7) / 3 + 1;
+  g.gw = (w4 + 2 * 3 - 7) / 3 + 1;
+  g.nh = pp_ceil_div(g.gh, WIN_H) * WIN_H;
+  g.nw = pp_ceil_div(g.gw, WIN_W) * WIN_W;
+  g.ph = (g.nh - 4) / 4 + 1;
+  g.pw = (g.nw - 4) / 4 + 1;
+  PP_TRY(pp_alloc(e, &g.enc, (size_t)T * P4 * 128, "encoder cache"));
+  PP_TRY(pp_alloc(e, &g.flows_f4, (size_t)(T - 1) * P4 * 2, "flows_f/4"));
+  PP_TRY(pp_alloc(e, &g.flows_b4, (size_t)(T - 1) * P4 * 2, "flows_b/4"));
+  PP_TRY(pp_alloc(e, &g.mask_in4, (size_t)T * P4 * 8, "mask2/4"));
+  g.mask_upd4 = nullptr;
+  const int n_win = (g.nh / WIN_H) * (g.nw / WIN_W);
+  PP_TRY(pp_alloc(e, &g.ring_idx, (size_t)n_win * RING, "ring indices"));
+  PP_TRY(pp_alloc(e, &g.win_flags, (size_t)n_win, "window flags"));
+  pp_build_ring_indices(g.nh, g.nw, g.ring_idx_host);
+  PP_CUDA_CHECK(cudaMemcpyAsync(g.ring_idx, g.ring_idx_host.data(), g.ring_idx_host.size() * sizeof(int),
+                                cudaMemcpyHostToDevice, st));
+  // 1/4-res flows (bilinear, /4) and masks (nearest); mask2 = (mask_in, mask_updated, 0 x6) per pixel
+  PP_TRY(pp_k_downsample_flow4(flows_f, g.flows_f4, T - 1, H, W, st));
+  PP_TRY(pp_k_downsample_flow4(flows_b, g.flows_b4, T - 1, H, W, st));
+  PP_CUDA_CHECK(cudaMemsetAsync(g.mask_in4, 0, (size_t)T * P4 * 8 * sizeof(__half), st));
+  PP_TRY(pp_k_downsample_mask4(masks_in, g.mask_in4, 8, 0, T, H, W, st));
+  PP_TRY(pp_k_downsample_mask4(masks_upd, g.mask_in4, 8, 1, T, H, W, st));
+  e.launches += 5;
+
+  // ---- Encoder (propainter.py:234-275) on all frames, in chunks bounded by workspace
+  const size_t m1 = e.arena.mark();
+  long long per_frame = (long long)H * W * 8 + (long long)h2 * w2 * 64 * 2 + P4 * (128 + 256 + 384 + 512 + 384 + 256);
+  long long avail = (long long)(e.arena.cap - e.arena.off) / 2 * 9 / 10;  // elements of fp16
+  int chunk = (int)(avail / per_frame);
+  if (chunk > T) chunk = T;
+  if (chunk > 32) chunk = 32;
+  PP_REQUIRE(chunk >= 1, "generator: workspace too small for the encoder");
+  __half *x8, *a0, *a1, *a2, *x0, *b8, *b10, *b12, *b14;
+  PP_TRY(pp_alloc(e, &x8, (size_t)chunk * H * W * 8, "enc input"));
+  PP_TRY(pp_alloc(e, &a0, (size_t)chunk * h2 * w2 * 64, "enc a0"));
+  PP_TRY(pp_alloc(e, &a1, (size_t)chunk * h2 * w2 * 64, "enc a1"));
+  PP_TRY(pp_alloc(e, &a2, (size_t)chunk * P4 * 128, "enc a2"));
+  PP_TRY(pp_alloc(e, &x0, (size_t)chunk * P4 * 256, "enc x0"));
+  PP_TRY(pp_alloc(e, &b8, (size_t)chunk * P4 * 384, "enc b8"));
+  PP_TRY(pp_alloc(e, &b10, (size_t)chunk * P4 * 512, "enc b10"));
+  PP_TRY(pp_alloc(e, &b12, (size_t)chunk * P4 * 384, "enc b12"));
+  PP_TRY(pp_alloc(e, &b14, (size_t)chunk * P4 * 256, "enc b14"));
+  const long long HW = (long long)H * W;
+  for (int f0 = 0; f0 < T; f0 += chunk) {
+    const int n = (f0 + chunk <= T) ? chunk : T - f0;
+    // input = cat(frame[3], mask_in[1], mask_updated[1]) (propainter.py:374-383), padded to 8 channels
+    PP_TRY(pp_k_nchw_f32_to_nhwc_f16(frames + (size_t)f0 * 3 * HW, x8, n, 3, H, W, 8, 0, 8, st));
+    PP_TRY(pp_k_nchw_f32_to_nhwc_f16(masks_in + (size_t)f0 * HW, x8, n, 1, H, W, 8, 3, 1, st));
+    PP_TRY(pp_k_nchw_f32_to_nhwc_f16(masks_upd + (size_t)f0 * HW, x8, n, 1, H, W, 8, 4, 1, st));
+    e.launches += 3;
+    const float s = 0.2f;
+    PP_TRY(PPConvCall(e, "gen.encoder.0", n, H, W).in(x8, 8, 0, 8).geom(2, 2, 1, 1).out(a0, 64, 0).act(PP_ACT_LRELU, s).run(st));
+    PP_TRY(PPConvCall(e, "gen.encoder.2", n, h2, w2).in(a0, 64, 0, 64).out(a1, 64, 0).act(PP_ACT_LRELU, s).run(st));
+    PP_TRY(PPConvCall(e, "gen.encoder.4", n, h2, w2).in(a1, 64, 0, 64).geom(2, 2, 1, 1).out(a2, 128, 0).act(PP_ACT_LRELU, s).run(st));
+    PP_TRY(PPConvCall(e, "gen.encoder.6", n, h4, w4).in(a2, 128, 0, 128).out(x0, 256, 0).act(PP_ACT_LRELU, s).run(st));
+    PP_TRY(PPConvCall(e, "gen.encoder.8", n, h4, w4).in(x0, 256, 0, 256).out(b8, 384, 0).act(PP_ACT_LRELU, s).run(st));
+    // grouped layers: group k sees cat(x0[k-th slice], out[k-th slice]) (propainter.py:268-273)
+    PP_TRY(PPConvCall(e, "gen.encoder.10", n, h4, w4).in(x0, 256, 0, 128, 128).in(b8, 384, 0, 192, 192)
+               .out(b10, 512, 0, 0, 256).act(PP_ACT_LRELU, s).run(st));
+    PP_TRY(PPConvCall(e, "gen.encoder.12", n, h4, w4).in(x0, 256, 0, 64, 64).in(b10, 512, 0, 128, 128)
+               .out(b12, 384, 0, 0, 96).act(PP_ACT_LRELU, s).run(st));
+    PP_TRY(PPConvCall(e, "gen.encoder.14", n, h4, w4).in(x0, 256, 0, 32, 32).in(b12, 384, 0, 48, 48)
+               .out(b14, 256, 0, 0, 32).act(PP_ACT_LRELU, s).run(st));
+    PP_TRY(PPConvCall(e, "gen.encoder.16", n, h4, w4).in(x0, 256, 0, 256).in(b14, 256, 0, 256)
+               .out(g.enc + (size_t)f0 * P4 * 128, 128, 0).act(PP_ACT_LRELU, s).run(st));
+  }
+  e.arena.release(m1);
+  return PP_OK;
+}
+
+int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __half* pred, cudaStream_t st) {
+  PPEngine::GenSession& g = e.gen;
+  PP_REQUIRE(g.active, "generator: pp_gen_begin was not called");
+  PP_REQUIRE(l_t >= 1 && l_t <= t, "generator: l_t=%d t=%d", l_t, t);
+  for (int i = 0; i < t; ++i) PP_REQUIRE(frame_ids[i] >= 0 && frame_ids[i] < g.T, "generator: frame id out of range");
+  for (int i = 1; i < l_t; ++i)
+    PP_REQUIRE(frame_ids[i] == frame_ids[0] + i, "generator: local frames must be consecutive");
+  const int H = g.H, W = g.W, h4 = H / 4, w4 = W / 4, h2 = H / 2, w2 = W / 2;
+  const long long P4 = (long long)h4 * w4;
+  const int gh = g.gh, gw = g.gw, nh = g.nh, nw = g.nw, ng = gh * gw, np = g.ph * g.pw;
+  const int f0 = frame_ids[0];
+  const size_t mark0 = e.arena.mark();
+  const size_t fsz = (size_t)P4 * 128;
+
+  // ---- learnable bidirectional feature propagation on the local frames (propainter.py:118-231) ------
+  const __half* x_local = g.enc + (size_t)f0 * fsz;
+  const __half* mask2 = g.mask_in4 + (size_t)f0 * P4 * 8;
+  __half *ob, *of, *cond, *o1, *o2, *offs, *cols, *aligned, *bb, *encw;
+  PP_TRY(pp_alloc(e, &ob, (size_t)l_t * fsz, "featprop backward"));
+  PP_TRY(pp_alloc(e, &of, (size_t)l_t * fsz, "featprop forward"));
+  PP_TRY(pp_alloc(e, &cond, (size_t)P4 * 264, "featprop cond"));
+  PP_TRY(pp_alloc(e, &o1, fsz, "featprop o1"));
+  PP_TRY(pp_alloc(e, &o2, fsz, "featprop o2"));
+  PP_TRY(pp_alloc(e, &offs, (size_t)P4 * 432, "featprop offsets"));
+  PP_TRY(pp_alloc(e, &cols, (size_t)P4 * 1152, "featprop dcn columns"));
+  PP_TRY(pp_alloc(e, &aligned, fsz, "featprop aligned"));
+  PP_TRY(pp_alloc(e, &bb, (size_t)l_t * fsz, "featprop tmp"));
+  PP_TRY(pp_alloc(e, &encw, (size_t)t * fsz, "window features"));
+  for (int mod = 0; mod < 2; ++mod) {
+    const std::string m = mod == 0 ? "gen.fp.backward_1" : "gen.fp.forward_1";
+    const __half* src = mod == 0 ? x_local : ob;  // the forward pass consumes the backward outputs
+    __half* dst = mod == 0 ? ob : of;
+    for (int i = 0; i < l_t; ++i) {
+      const int idx = mod == 0 ? l_t - 1 - i : i;
+      const __half* cur = src + (size_t)idx * fsz;
+      const __half* m2 = mask2 + (size_t)idx * P4 * 8;
+      const __half* prop = cur;
+      if (i > 0) {
+        const int prev = mod == 0 ? idx + 1 : idx - 1;
+        const int fi = mod == 0 ? idx : idx - 1;  // flow index
+        const __half* fprop = (mod == 0 ? g.flows_f4 : g.flows_b4) + (size_t)(f0 + fi) * P4 * 2;
+        const __half* fchk = (mod == 0 ? g.flows_b4 : g.flows_f4) + (size_t)(f0 + fi) * P4 * 2;
+        const __half* pprev = dst + (size_t)prev * fsz;
+        PP_TRY(pp_k_featprop_cond(cur, 128, pprev, 128, fprop, fchk, m2, 8, cond, 264, h4, w4, 128, st));
+        e.launches++;
+        PP_TRY(PPConvCall(e, m + ".offset.0", 1, h4, w4).in(cond, 264, 0, 264).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
+        PP_TRY(PPConvCall(e, m + ".offset.1", 1, h4, w4).in(o1, 128, 0, 128).out(o2, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
+        PP_TRY(PPConvCall(e, m + ".offset.2", 1, h4, w4).in(o2, 128, 0, 128).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
+        PP_TRY(PPConvCall(e, m + ".offset.3", 1, h4, w4).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
+        // offsets = 3*tanh(.) + flow (dy,dx) (propainter.py:66-68); flow sits at cond[:, 256:258]
+        PP_TRY(pp_k_dcn_sample(pprev, 128, 0, 128, nullptr, 0, 0, 0, offs, 432, cond, 264, 256, 3.0f, cols, 1, h4, w4, st));
+        e.launches++;
+        PP_TRY(PPConvCall(e, m + ".dcn", 1, h4, w4).in(cols, 1152, 0, 1152).geom(1, 1, 0, 0).out(aligned, 128, 0).run(st));
+        prop = aligned;
+      }
+      // feat_prop = feat_prop + backbone(cat(cur, feat_prop, mask_current))
+      PP_TRY(PPConvCall(e, m + ".backbone.0", 1, h4, w4).in(cur, 128, 0, 128).in(prop, 128, 0, 128).in(m2, 8, 0, 8)
+                 .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+      PP_TRY(PPConvCall(e, m + ".backbone.1", 1, h4, w4).in(bb, 128, 0, 128).out(dst + (size_t)idx * fsz, 128, 0)
+                 .residual(prop, 128, 0).run(st));
+    }
+  }
+  // fuse(cat(out_b, out_f, mask)) + x  -> local part of the window features
+  PP_TRY(PPConvCall(e, "gen.fp.fuse.0", l_t, h4, w4).in(ob, 128, 0, 128).in(of, 128, 0, 128).in(mask2, 8, 0, 8)
+             .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(PPConvCall(e, "gen.fp.fuse.1", l_t, h4, w4).in(bb, 128, 0, 128).out(encw, 128, 0)
+             .residual(x_local, 128, 0).run(st));
+  for (int i = l_t; i < t; ++i)
+    PP_CUDA_CHECK(cudaMemcpyAsync(encw + (size_t)i * fsz, g.enc + (size_t)frame_ids[i] * fsz, fsz * sizeof(__half),
+                                  cudaMemcpyDeviceToDevice, st));
+
+  // ---- SoftSplit: unfold(7,3,3) + Linear == 7x7 stride-3 conv (sparse_transformer.py:8-36) ------------
+  const long long rows = (long long)t * ng, rows_pad = (long long)t * nh * nw;
+  __half *x, *xn, *qkv, *pooled, *pkv, *att, *y, *f1, *img40;
+  PP_TRY(pp_alloc(e, &x, (size_t)rows * 512, "tokens"));
+  PP_TRY(pp_alloc(e, &xn, (size_t)rows_pad * 512, "normed tokens"));
+  PP_TRY(pp_alloc(e, &qkv, (size_t)rows_pad * 1536, "qkv"));
+  PP_TRY(pp_alloc(e, &pooled, (size_t)t * np * 512, "pooled tokens"));
+  PP_TRY(pp_alloc(e, &pkv, (size_t)t * np * 1024, "pooled kv"));
+  PP_TRY(pp_alloc(e, &att, (size_t)rows * 512, "attention out"));
+  PP_TRY(pp_alloc(e, &y, (size_t)rows * 512, "normed tokens 2"));
+  PP_TRY(pp_alloc(e, &f1, (size_t)rows * 1960, "ffn hidden"));
+  PP_TRY(pp_alloc(e, &img40, (size_t)t * P4 * 40, "ffn folded"));
+  PP_TRY(PPConvCall(e, "gen.ss", t, h4, w4).in(encw, 128, 0, 128).geom(3, 3, 3, 3).out(x, 512, 0).run(st));
+  if (nh != gh || nw != gw) PP_CUDA_CHECK(cudaMemsetAsync(xn, 0, (size_t)rows_pad * 512 * sizeof(__half), st));
+  // window dispatch flags from the local frames' original masks (propainter.py:417-428)
+  PP_TRY(pp_k_window_flags(mask2, 8, 0, l_t, h4, w4, gh, gw, nh / WIN_H, nw / WIN_W, g.win_flags, st));
+  e.launches++;
+
+  for (int blk = 0; blk < 8; ++blk) {
+    const std::string b = "gen.tf." + std::to_string(blk) + ".";
+    const void *g1, *b1, *g2, *b2, *pwt, *pbs;
+    PP_TRY(pp_get_tensor(e, b + "norm1.weight", &g1));
+    PP_TRY(pp_get_tensor(e, b + "norm1.bias", &b1));
+    PP_TRY(pp_get_tensor(e, b + "norm2.weight", &g2));
+    PP_TRY(pp_get_tensor(e, b + "norm2.bias", &b2));
+    PP_TRY(pp_get_tensor(e, b + "pool.weight", &pwt));
+    PP_TRY(pp_get_tensor(e, b + "pool.bias", &pbs));
+    PP_TRY(pp_k_layernorm(x, (const float*)g1, (const float*)b1, xn, rows, gh, gw, nh, nw, st));
+    PP_TRY(PPConvCall(e, b + "qkv", 1, 1, (int)rows_pad).in(xn, 512, 0, 512).out(qkv, 1536, 0).run(st));
+    PP_TRY(pp_k_pool_tokens(xn, (const float*)pwt, (const float*)pbs, pooled, t, nh, nw, g.ph, g.pw, 512, st));
+    PP_TRY(PPConvCall(e, b + "kv", 1, 1, t * np).in(pooled, 512, 0, 512).out(pkv, 1024, 0).run(st));
+    PP_TRY(pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, att, 512, g.win_flags, g.ring_idx, t,
+                          gh, gw, nh, nw, np, blk % 2, st));
+    PP_TRY(PPConvCall(e, b + "proj", 1, 1, (int)rows).in(att, 512, 0, 512).out(x, 512, 0).residual(x, 512, 0).run(st));
+    PP_TRY(pp_k_layernorm(x, (const float*)g2, (const float*)b2, y, rows, gh, gw, gh, gw, st));
+    // FusionFeedForward (sparse_transformer.py:67-123): fc1 -> fold/normalise/(unfold) -> GELU -> fc2
+    PP_TRY(PPConvCall(e, b + "fc1", 1, 1, (int)rows).in(y, 512, 0, 512).out(f1, 1960, 0).run(st));
+    PP_TRY(pp_k_fold(f1, 1960, img40, t, h4, w4, 40, gh, gw, 1, 1, st));
+    PP_TRY(PPConvCall(e, b + "fc2", t, h4, w4).in(img40, 40, 0, 40).geom(3, 3, 3, 3).out(x, 512, 0)
+               .residual(x, 512, 0).run(st));
+    e.launches += 5;
+  }
+
+  // ---- SoftComp on the local frames only (decoder input), + residual (propainter.py:440-451) -----------
+  __half *sc1, *img128, *encf;
+  PP_TRY(pp_alloc(e, &sc1, (size_t)l_t * ng * 6272, "softcomp linear"));
+  PP_TRY(pp_alloc(e, &img128, (size_t)l_t * fsz, "softcomp folded"));
+  PP_TRY(pp_alloc(e, &encf, (size_t)l_t * fsz, "decoder input"));
+  PP_TRY(PPConvCall(e, "gen.sc.embedding", 1, 1, l_t * ng).in(x, 512, 0, 512).out(sc1, 6272, 0).run(st));
+  PP_TRY(pp_k_fold(sc1, 6272, img128, l_t, h4, w4, 128, gh, gw, 0, 0, st));
+  e.launches++;
+  PP_TRY(PPConvCall(e, "gen.sc.bias_conv", l_t, h4, w4).in(img128, 128, 0, 128).out(encf, 128, 0)
+             .residual(encw, 128, 0).run(st));
+
+  // ---- decoder (propainter.py:304-312) + tanh ------------------------------------------------------------
+  __half *up, *d0, *d1, *d2;
+  PP_TRY(pp_alloc(e, &up, (size_t)l_t * H * W * 64, "decoder upsampled"));
+  PP_TRY(pp_alloc(e, &d0, (size_t)l_t * h2 * w2 * 128, "decoder d0"));
+  PP_TRY(pp_alloc(e, &d1, (size_t)l_t * h2 * w2 * 64, "decoder d1"));
+  PP_TRY(pp_alloc(e, &d2, (size_t)l_t * H * W * 64, "decoder d2"));
+  PP_TRY(deconv(e, "gen.decoder.0", encf, l_t, h4, w4, 128, up, d0, 128, 128, PP_ACT_LRELU, 0.2f, st));
+  PP_TRY(PPConvCall(e, "gen.decoder.2", l_t, h2, w2).in(d0, 128, 0, 128).out(d1, 64, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(deconv(e, "gen.decoder.4", d1, l_t, h2, w2, 64, up, d2, 64, 64, PP_ACT_LRELU, 0.2f, st));
+  PP_TRY(PPConvCall(e, "gen.decoder.6", l_t, H, W).in(d2, 64, 0, 64).out(pred, 4, 0).act(PP_ACT_TANH).run(st));
+  e.arena.release(mark0);
+  return PP_OK;
+}

@@ -1,0 +1,431 @@
+// Flow-guided propagation kernels: fused image-propagation step, flow warps, fb-consistency,
+// modulated deformable sampling, flow-completion pack/combine, 1/4 downsampling.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblocks(long long n, int per = TPB) { return (int)((n + per - 1) / per); }
+
+// Sampling position of grid_sample(align_corners=True) for pixel coordinate (x + flow): the reference
+// normalises with 2*g/max(W-1,1)-1 (flow_loss_utils.py:41-43) and ATen's CUDA sampler un-normalises with
+// ((g+1)/2)*(W-1).  The round trip is kept (no FMA contraction) so `nearest` picks the same texel.
+__device__ __forceinline__ float sample_coord(float g, int size) {
+  const float d = (float)max(size - 1, 1);
+  const float nrm = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, g), d), 1.0f);
+  return __fmul_rn(__fdiv_rn(__fadd_rn(nrm, 1.0f), 2.0f), (float)(size - 1));
+}
+
+struct Bilin {
+  int x0, y0;
+  float w00, w01, w10, w11;  // weights, already zero for out-of-range corners
+};
+
+__device__ __forceinline__ Bilin bilin_setup(float sx, float sy, int W, int H) {
+  Bilin b;
+  const float fx = floorf(sx), fy = floorf(sy);
+  b.x0 = (int)fx; b.y0 = (int)fy;
+  const float ax = sx - fx, ay = sy - fy;
+  const bool x0in = b.x0 >= 0 && b.x0 < W, x1in = b.x0 + 1 >= 0 && b.x0 + 1 < W;
+  const bool y0in = b.y0 >= 0 && b.y0 < H, y1in = b.y0 + 1 >= 0 && b.y0 + 1 < H;
+  b.w00 = (y0in && x0in) ? (1.f - ax) * (1.f - ay) : 0.f;
+  b.w01 = (y0in && x1in) ? ax * (1.f - ay) : 0.f;
+  b.w10 = (y1in && x0in) ? (1.f - ax) * ay : 0.f;
+  b.w11 = (y1in && x1in) ? ax * ay : 0.f;
+  return b;
+}
+
+// bilinear sample of a 2-channel fp16 flow field [H][W][2]
+__device__ __forceinline__ float2 sample_flow2(const __half2* f, const Bilin& b, int W) {
+  float2 r = make_float2(0.f, 0.f);
+  if (b.w00 != 0.f) { const float2 v = __half22float2(f[b.y0 * W + b.x0]); r.x += b.w00 * v.x; r.y += b.w00 * v.y; }
+  if (b.w01 != 0.f) { const float2 v = __half22float2(f[b.y0 * W + b.x0 + 1]); r.x += b.w01 * v.x; r.y += b.w01 * v.y; }
+  if (b.w10 != 0.f) { const float2 v = __half22float2(f[(b.y0 + 1) * W + b.x0]); r.x += b.w10 * v.x; r.y += b.w10 * v.y; }
+  if (b.w11 != 0.f) { const float2 v = __half22float2(f[(b.y0 + 1) * W + b.x0 + 1]); r.x += b.w11 * v.x; r.y += b.w11 * v.y; }
+  return r;
+}
+
+// fbConsistencyCheck (model/propainter.py:27-36): |f_p + warp(f_c, f_p)|^2 < 0.01(|f_p|^2 + |warp|^2) + 0.5
+__device__ __forceinline__ float fb_valid(float2 fp, float2 fcw) {
+  const float dx = fp.x + fcw.x, dy = fp.y + fcw.y;
+  const float mag = fp.x * fp.x + fp.y * fp.y + fcw.x * fcw.x + fcw.y * fcw.y;
+  return (dx * dx + dy * dy) < (0.01f * mag + 0.5f) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One time step of the non-learnable image propagation (BidirectionalPropagation(3, learnable=False),
+// model/propainter.py:157-196), fully fused: fb check, nearest warp of the propagated pixels, bilinear
+// warp + 0.1 threshold of the propagated mask, mask algebra, blend.
+// Pixel layout: 4 x fp16 = (r, g, b, mask) so one 8-byte access moves a whole pixel.
+// Algorithmic traffic: cur 8 B + prop gather 8 B (+ 3 more mask taps) + out 8 B + 2 flows 4 B each.
+// ------------------------------------------------------------------------------------------------
+__global__ void imgprop_step(const uint2* __restrict__ cur, const uint2* __restrict__ prop_in,
+                             uint2* __restrict__ prop_out, const __half2* __restrict__ flow_prop,
+                             const __half2* __restrict__ flow_check, int H, int W) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W) return;
+  const int x = idx % W, y = idx / W;
+  const float2 fp = __half22float2(flow_prop[idx]);
+  const float sx = sample_coord((float)x + fp.x, W), sy = sample_coord((float)y + fp.y, H);
+  const Bilin b = bilin_setup(sx, sy, W, H);
+  const float valid = fb_valid(fp, sample_flow2(flow_check, b, W));
+  // nearest texel of the propagated frame
+  const int nx = (int)nearbyintf(sx), ny = (int)nearbyintf(sy);
+  float wr = 0.f, wg = 0.f, wb = 0.f;
+  if (nx >= 0 && nx < W && ny >= 0 && ny < H) {
+    const uint2 t = prop_in[ny * W + nx];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    wr = a.x; wg = a.y; wb = c.x;
+  }
+  // bilinear sample of the propagated mask (4th channel)
+  float mw = 0.f;
+  if (b.w00 != 0.f) mw += b.w00 * __half2float(reinterpret_cast<const __half*>(&prop_in[b.y0 * W + b.x0])[3]);
+  if (b.w01 != 0.f) mw += b.w01 * __half2float(reinterpret_cast<const __half*>(&prop_in[b.y0 * W + b.x0 + 1])[3]);
+  if (b.w10 != 0.f) mw += b.w10 * __half2float(reinterpret_cast<const __half*>(&prop_in[(b.y0 + 1) * W + b.x0])[3]);
+  if (b.w11 != 0.f) mw += b.w11 * __half2float(reinterpret_cast<const __half*>(&prop_in[(b.y0 + 1) * W + b.x0 + 1])[3]);
+  const float mv = mw > 0.1f ? 1.f : 0.f;
+  const uint2 cu = cur[idx];
+  const float2 c01 = __half22float2(*reinterpret_cast<const __half2*>(&cu.x));
+  const float2 c23 = __half22float2(*reinterpret_cast<const __half2*>(&cu.y));
+  const float mcur = c23.y;
+  const float u = (mcur * valid * (1.f - mv)) > 0.1f ? 1.f : 0.f;
+  const float mnew = (mcur * (1.f - valid * (1.f - mv))) > 0.1f ? 1.f : 0.f;
+  const float r = u * wr + (1.f - u) * c01.x, g = u * wg + (1.f - u) * c01.y, bb = u * wb + (1.f - u) * c23.x;
+  uint2 o;
+  *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(r, g);
+  *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(bb, mnew);
+  prop_out[idx] = o;
+}
+
+// frames [T,3,H,W] f32 (already multiplied by (1-mask) here) + masks -> [T][H][W][4] fp16
+__global__ void imgprop_pack(const float* __restrict__ frames, const float* __restrict__ masks,
+                             uint2* __restrict__ dst, long long HW, long long total) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long t = idx / HW, p = idx - t * HW;
+  const float m = masks[idx];
+  const float* f = frames + t * 3 * HW + p;
+  const float k = 1.f - m;
+  uint2 o;
+  *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(f[0] * k, f[HW] * k);
+  *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(f[2 * HW] * k, m);
+  dst[idx] = o;
+}
+
+// updated = frames*(1-m) + prop*m ; updated mask = propagated mask   (propainter_inference.py:213-219)
+__global__ void imgprop_finish(const uint2* __restrict__ prop, const float* __restrict__ frames,
+                               const float* __restrict__ masks, float* __restrict__ uf, float* __restrict__ um,
+                               long long HW, long long total) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long t = idx / HW, p = idx - t * HW;
+  const uint2 v = prop[idx];
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  const float m = masks[idx], k = 1.f - m;
+  const float* f = frames + t * 3 * HW + p;
+  float* o = uf + t * 3 * HW + p;
+  o[0] = f[0] * k + a.x * m;
+  o[HW] = f[HW] * k + a.y * m;
+  o[2 * HW] = f[2 * HW] * k + c.x * m;
+  um[idx] = c.y;
+}
+
+// [n,2,H,W] f32 -> [n][H][W][2] fp16
+__global__ void flow_to_nhwc2(const float* __restrict__ src, __half2* __restrict__ dst, long long HW,
+                              long long total) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long n = idx / HW, p = idx - n * HW;
+  dst[idx] = __floats2half2_rn(src[(n * 2) * HW + p], src[(n * 2 + 1) * HW + p]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flow completion input: cat(flow * (1 - mask), mask) per frame (recurrent_flow_completion.py:361-366, 320-323),
+// optionally time-reversed (backward flows are flipped before the network, :375-376).  -> [T][H][W][8] fp16.
+// ------------------------------------------------------------------------------------------------
+__global__ void rfc_pack_input(const float* __restrict__ flows, const float* __restrict__ masks,
+                               uint4* __restrict__ dst, int T, long long HW, int reverse, long long dst_tstride) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * HW) return;
+  const long long t = idx / HW, p = idx - t * HW;
+  const long long ts = reverse ? (T - 1 - t) : t;
+  const float m = masks[ts * HW + p];
+  const float k = 1.f - m;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(flows[(ts * 2) * HW + p] * k, flows[(ts * 2 + 1) * HW + p] * k);
+  *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(m, 0.f);
+  dst[t * dst_tstride + p] = o;
+}
+
+// combine_flow (recurrent_flow_completion.py:389-400): out = pred*m + gt*(1-m), un-reversing time.
+__global__ void rfc_combine(const __half* __restrict__ pred, int pred_cs, const float* __restrict__ gt,
+                            const float* __restrict__ masks, float* __restrict__ out, int T, long long HW,
+                            int reverse, long long pred_tstride) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * HW) return;
+  const long long t = idx / HW, p = idx - t * HW;
+  const long long ts = reverse ? (T - 1 - t) : t;  // network time index holding frame t
+  const __half* pr = pred + (ts * pred_tstride + p) * pred_cs;
+  const float m = masks[idx], k = 1.f - m;
+  out[(t * 2) * HW + p] = __half2float(pr[0]) * m + gt[(t * 2) * HW + p] * k;
+  out[(t * 2 + 1) * HW + p] = __half2float(pr[1]) * m + gt[(t * 2 + 1) * HW + p] * k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Modulated deformable sampling (torchvision.ops.deform_conv2d im2col stage; call sites
+// recurrent_flow_completion.py:44-53 and propainter.py:73-82), 3x3, stride 1, pad 1, dil 1, 16 offset groups.
+// offs row = raw output of conv_offset[-1]: channels [0,288) -> offsets, (g*9+k)*2+{0:dy,1:dx}, passed through
+// max_mag*tanh (+ flow (dy,dx) for the feature path); channels [288,432) -> sigmoid modulation, g*9+k.
+// cols[m][k*C + c] = mask * bilinear(x[c], y-1+ky+dy, x-1+kx+dx); zero outside (h<=-1 || h>=H ...).
+// One thread per (pixel, tap, group): the 4 bilinear weights are computed once and applied to the
+// group's C/16 contiguous channels with 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+template <int CPG>  // channels per offset group: 8 or 16
+__global__ void dcn_sample(const __half* __restrict__ x0, int x0_cs, int x0_co, int C0,
+                           const __half* __restrict__ x1, int x1_cs, int x1_co,
+                           const __half* __restrict__ offs, int offs_cs, const __half* __restrict__ flow, int flow_cs,
+                           int flow_co, float max_mag, __half* __restrict__ cols, int C, int N, int H, int W) {
+  const long long total = (long long)N * H * W * 144;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gk = idx % 144;           // g*9 + k  (g-major like the offset channels)
+  const long long m = idx / 144;
+  const int g = gk / 9, k = gk - g * 9;
+  const int x = m % W;
+  const long long t = m / W;
+  const int y = t % H;
+  const int n = t / H;
+  const __half* o = offs + m * offs_cs;
+  float dy = max_mag * tanhf(__half2float(o[2 * gk]));
+  float dx = max_mag * tanhf(__half2float(o[2 * gk + 1]));
+  if (flow != nullptr) {
+    dx += __half2float(flow[m * flow_cs + flow_co]);
+    dy += __half2float(flow[m * flow_cs + flow_co + 1]);
+  }
+  const float mod = 1.f / (1.f + __expf(-__half2float(o[288 + gk])));
+  const float py = (float)(y - 1 + k / 3) + dy, px = (float)(x - 1 + k % 3) + dx;
+  float acc[CPG];
+#pragma unroll
+  for (int i = 0; i < CPG; ++i) acc[i] = 0.f;
+  if (py > -1.f && py < (float)H && px > -1.f && px < (float)W) {
+    const float fy = floorf(py), fx = floorf(px);
+    const int y0 = (int)fy, xx0 = (int)fx;
+    const float ay = py - fy, ax = px - fx;
+    const int c = g * CPG;  // channel inside cat(x0, x1)
+    const __half* src;
+    int cs;
+    if (c < C0) { src = x0 + x0_co + c; cs = x0_cs; }
+    else { src = x1 + x1_co + (c - C0); cs = x1_cs; }
+    src += (long long)n * H * W * cs;
+#pragma unroll
+    for (int corner = 0; corner < 4; ++corner) {
+      const int yy = y0 + (corner >> 1), xx = xx0 + (corner & 1);
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
+      const uint4* vp = reinterpret_cast<const uint4*>(src + ((long long)yy * W + xx) * cs);
+#pragma unroll
+      for (int v = 0; v < CPG / 8; ++v) {
+        const uint4 q = vp[v];
+        const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(hq[e]);
+          acc[v * 8 + 2 * e] += w * f.x;
+          acc[v * 8 + 2 * e + 1] += w * f.y;
+        }
+      }
+    }
+  }
+  __half* d = cols + m * (long long)(9 * C) + k * C + g * CPG;
+#pragma unroll
+  for (int v = 0; v < CPG / 8; ++v) {
+    __align__(16) __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(mod * acc[v * 8 + 2 * e], mod * acc[v * 8 + 2 * e + 1]);
+    reinterpret_cast<uint4*>(d)[v] = *reinterpret_cast<uint4*>(h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Learnable feature propagation, per step (model/propainter.py:157-176): fb check of the 1/4-res flows,
+// bilinear warp of the propagated feature, and assembly of the DCN condition
+//   cond = cat(cur[C], warped[C], flow[2], valid[1], mask_cur[2])  -> [H][W][2C+8] (3 pad channels = 0)
+// One thread per (pixel, 8-channel vector of C); vector 0 also writes the 5 scalar channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void featprop_cond(const __half* __restrict__ cur, int cur_cs, const __half* __restrict__ prop,
+                              int prop_cs, const __half2* __restrict__ flow_prop,
+                              const __half2* __restrict__ flow_check, const __half* __restrict__ mask2,
+                              int mask_cs, __half* __restrict__ cond, int cond_cs, int H, int W, int C) {
+  const int C8 = C / 8;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)H * W * C8) return;
+  const int c8 = idx % C8;
+  const int p = idx / C8;
+  const int x = p % W, y = p / W;
+  const float2 fp = __half22float2(flow_prop[p]);
+  const float sx = sample_coord((float)x + fp.x, W), sy = sample_coord((float)y + fp.y, H);
+  const Bilin b = bilin_setup(sx, sy, W, H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const float ws[4] = {b.w00, b.w01, b.w10, b.w11};
+#pragma unroll
+  for (int corner = 0; corner < 4; ++corner) {
+    if (ws[corner] == 0.f) continue;
+    const int yy = b.y0 + (corner >> 1), xx = b.x0 + (corner & 1);
+    const uint4 q = *reinterpret_cast<const uint4*>(prop + ((long long)yy * W + xx) * prop_cs + c8 * 8);
+    const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(hq[e]);
+      acc[2 * e] += ws[corner] * f.x;
+      acc[2 * e + 1] += ws[corner] * f.y;
+    }
+  }
+  __half* cp = cond + (long long)p * cond_cs;
+  *reinterpret_cast<uint4*>(cp + c8 * 8) = *reinterpret_cast<const uint4*>(cur + (long long)p * cur_cs + c8 * 8);
+  __align__(16) __half2 h[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+  *reinterpret_cast<uint4*>(cp + C + c8 * 8) = *reinterpret_cast<uint4*>(h);
+  if (c8 == 0) {
+    const float valid = fb_valid(fp, sample_flow2(flow_check, b, W));
+    const float2 mk = __half22float2(*reinterpret_cast<const __half2*>(mask2 + (long long)p * mask_cs));
+    __align__(16) __half2 s[4];
+    s[0] = __floats2half2_rn(fp.x, fp.y);
+    s[1] = __floats2half2_rn(valid, mk.x);
+    s[2] = __floats2half2_rn(mk.y, 0.f);
+    s[3] = __floats2half2_rn(0.f, 0.f);
+    *reinterpret_cast<uint4*>(cp + 2 * C) = *reinterpret_cast<uint4*>(s);
+  }
+}
+
+// F.interpolate(scale_factor=1/4, bilinear, align_corners=False) == mean of the centre 2x2 of each 4x4 block;
+// the reference then divides the flow by 4 (propainter.py:389-406).  [n,2,H,W] f32 -> [n][H/4][W/4][2] fp16.
+__global__ void downsample_flow4(const float* __restrict__ src, __half2* __restrict__ dst, int n, int H, int W) {
+  const int h = H / 4, w = W / 4;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * h * w) return;
+  const int x = idx % w;
+  long long t = idx / w;
+  const int y = t % h;
+  const int i = t / h;
+  float v[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float* s = src + ((long long)(i * 2 + c) * H + 4 * y + 1) * W + 4 * x + 1;
+    v[c] = 0.25f * (0.25f * (s[0] + s[1] + s[W] + s[W + 1]));
+  }
+  dst[idx] = __floats2half2_rn(v[0], v[1]);
+}
+
+// F.interpolate(scale_factor=1/4, 'nearest') picks source index 4*i.  [n,1,H,W] f32 -> fp16 slice.
+__global__ void downsample_mask4(const float* __restrict__ src, __half* __restrict__ dst, int dst_cs, int dst_co,
+                                 int n, int H, int W) {
+  const int h = H / 4, w = W / 4;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * h * w) return;
+  const int x = idx % w;
+  long long t = idx / w;
+  const int y = t % h;
+  const int i = t / h;
+  dst[idx * dst_cs + dst_co] = __float2half_rn(src[((long long)i * H + 4 * y) * W + 4 * x]);
+}
+
+}  // namespace
+
+int pp_k_imgprop_step(const __half* cur, const __half* prop_in, __half* prop_out, const __half* flow_prop,
+                      const __half* flow_check, int H, int W, cudaStream_t st) {
+  imgprop_step<<<nblocks((long long)H * W), TPB, 0, st>>>(
+      reinterpret_cast<const uint2*>(cur), reinterpret_cast<const uint2*>(prop_in), reinterpret_cast<uint2*>(prop_out),
+      reinterpret_cast<const __half2*>(flow_prop), reinterpret_cast<const __half2*>(flow_check), H, W);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_imgprop_pack(const float* frames, const float* masks, __half* dst, int T, int H, int W, cudaStream_t st) {
+  const long long HW = (long long)H * W, total = HW * T;
+  imgprop_pack<<<nblocks(total), TPB, 0, st>>>(frames, masks, reinterpret_cast<uint2*>(dst), HW, total);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_imgprop_finish(const __half* prop, const float* frames, const float* masks, float* upd_frames,
+                        float* upd_masks, int T, int H, int W, cudaStream_t st) {
+  const long long HW = (long long)H * W, total = HW * T;
+  imgprop_finish<<<nblocks(total), TPB, 0, st>>>(reinterpret_cast<const uint2*>(prop), frames, masks, upd_frames,
+                                                 upd_masks, HW, total);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_flow_to_nhwc2(const float* src, __half* dst, int n, int H, int W, cudaStream_t st) {
+  const long long HW = (long long)H * W, total = HW * n;
+  if (total == 0) return PP_OK;
+  flow_to_nhwc2<<<nblocks(total), TPB, 0, st>>>(src, reinterpret_cast<__half2*>(dst), HW, total);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_rfc_pack_input(const float* flows, const float* masks, __half* dst, long long dst_tstride_pix, int T, int H,
+                        int W, int reverse_time, cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  rfc_pack_input<<<nblocks(HW * T), TPB, 0, st>>>(flows, masks, reinterpret_cast<uint4*>(dst), T, HW, reverse_time,
+                                                  dst_tstride_pix);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_rfc_combine(const __half* pred, int pred_cs, long long pred_tstride_pix, const float* gt, const float* masks,
+                     float* out, int T, int H, int W, int reverse_time, cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  rfc_combine<<<nblocks(HW * T), TPB, 0, st>>>(pred, pred_cs, gt, masks, out, T, HW, reverse_time, pred_tstride_pix);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half* x1, int x1_cs, int x1_co, int C1,
+                    const __half* offs, int offs_cs, const __half* flow, int flow_cs, int flow_co, float max_mag,
+                    __half* cols, int N, int H, int W, cudaStream_t st) {
+  const int C = C0 + C1;
+  PP_REQUIRE(C == 128 || C == 256, "dcn_sample: C=%d must be 128 or 256 (16 offset groups)", C);
+  PP_REQUIRE(C0 % 16 == 0, "dcn_sample: C0=%d", C0);
+  const long long total = (long long)N * H * W * 144;
+  if (C == 128)
+    dcn_sample<8><<<nblocks(total), TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow, flow_cs,
+                                                  flow_co, max_mag, cols, C, N, H, W);
+  else
+    dcn_sample<16><<<nblocks(total), TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow,
+                                                   flow_cs, flow_co, max_mag, cols, C, N, H, W);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_featprop_cond(const __half* cur, int cur_cs, const __half* prop, int prop_cs, const __half* flow_prop,
+                       const __half* flow_check, const __half* mask2, int mask_cs, __half* cond, int cond_cs, int H,
+                       int W, int C, cudaStream_t st) {
+  PP_REQUIRE(C % 8 == 0 && cond_cs >= 2 * C + 8, "featprop_cond: bad channel counts");
+  featprop_cond<<<nblocks((long long)H * W * (C / 8)), TPB, 0, st>>>(
+      cur, cur_cs, prop, prop_cs, reinterpret_cast<const __half2*>(flow_prop),
+      reinterpret_cast<const __half2*>(flow_check), mask2, mask_cs, cond, cond_cs, H, W, C);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_downsample_flow4(const float* flow, __half* dst, int n, int H, int W, cudaStream_t st) {
+  const long long total = (long long)n * (H / 4) * (W / 4);
+  if (total == 0) return PP_OK;
+  downsample_flow4<<<nblocks(total), TPB, 0, st>>>(flow, reinterpret_cast<__half2*>(dst), n, H, W);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_downsample_mask4(const float* m, __half* dst, int dst_cs, int dst_co, int n, int H, int W, cudaStream_t st) {
+  const long long total = (long long)n * (H / 4) * (W / 4);
+  if (total == 0) return PP_OK;
+  downsample_mask4<<<nblocks(total), TPB, 0, st>>>(m, dst, dst_cs, dst_co, n, H, W);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}

@@ -1,0 +1,287 @@
+// RAFT-specific HBM-bound kernels: instance norm, correlation pyramid pooling + 9x9x4 lookup,
+// GRU state plumbing, convex upsampling.  Reference call sites are cited per kernel.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblocks(long long n, int per = TPB) { return (int)((n + per - 1) / per); }
+
+// ------------------------------------------------------------------------------------------------
+// InstanceNorm2d(affine=False) statistics: per (image, channel) sum and sum of squares.
+// grid (chunks, N); block = 256 threads; thread t owns channel pair (t % (C/2)) and strides pixels.
+// (reference: RAFT/extractor.py fnet norm layers, F.instance_norm eps=1e-5, biased variance)
+// ------------------------------------------------------------------------------------------------
+__global__ void instnorm_stats(const __half* __restrict__ x, int HW, int C, float* __restrict__ sums,
+                               int pix_per_block) {
+  extern __shared__ float sm[];  // [2][C]
+  const int n = blockIdx.y;
+  const int C2 = C >> 1;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lanes = blockDim.x / C2;  // pixel lanes per block
+  const int cp = threadIdx.x % C2;
+  const int pl = threadIdx.x / C2;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (pl < lanes) {
+    const __half2* base = reinterpret_cast<const __half2*>(x + ((long long)n * HW) * C) + cp;
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const float2 v = __half22float2(base[(long long)p * C2]);
+      s0 += v.x; s1 += v.y; q0 += v.x * v.x; q1 += v.y * v.y;
+    }
+    atomicAdd(&sm[2 * cp], s0);
+    atomicAdd(&sm[2 * cp + 1], s1);
+    atomicAdd(&sm[C + 2 * cp], q0);
+    atomicAdd(&sm[C + 2 * cp + 1], q1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[(long long)n * 2 * C + i], sm[i]);
+}
+
+// out = [relu]( (x - mean) * rstd );  if residual: out = relu(residual + out)   (ResidualBlock tail)
+__global__ void instnorm_apply(const __half* __restrict__ x, const float* __restrict__ sums,
+                               const __half* __restrict__ residual, __half* __restrict__ out, int HW, int C,
+                               long long total2, int relu) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total2) return;
+  const int C2 = C >> 1;
+  const int cp = idx % C2;
+  const long long p = idx / C2;
+  const int n = p / HW;
+  const float inv = 1.f / (float)HW;
+  const float* s = sums + (long long)n * 2 * C;
+  const float m0 = s[2 * cp] * inv, m1 = s[2 * cp + 1] * inv;
+  const float v0 = fmaxf(s[C + 2 * cp] * inv - m0 * m0, 0.f), v1 = fmaxf(s[C + 2 * cp + 1] * inv - m1 * m1, 0.f);
+  const float r0 = rsqrtf(v0 + 1e-5f), r1 = rsqrtf(v1 + 1e-5f);
+  const float2 xv = __half22float2(reinterpret_cast<const __half2*>(x)[idx]);
+  float a = (xv.x - m0) * r0, b = (xv.y - m1) * r1;
+  if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+  if (residual != nullptr) {
+    const float2 rv = __half22float2(reinterpret_cast<const __half2*>(residual)[idx]);
+    a = fmaxf(a + rv.x, 0.f);
+    b = fmaxf(b + rv.y, 0.f);
+  }
+  reinterpret_cast<__half2*>(out)[idx] = __floats2half2_rn(a, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pack a row-major [G][R][K] fp16 matrix into the swizzled B-operand tile image consumed by the
+// tcgen05 GEMM ([G][K/64][R_pad] rows of 128 B, 16-byte chunk index XOR (row & 7)); rows >= R are zero.
+// Used for the all-pairs correlation, where fmap2 plays the role of the weights (RAFT/corr.py:52-60).
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_b_operand(const __half* __restrict__ src, __half* __restrict__ dst, int R, int R_pad, int K,
+                               long long total) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  if (idx >= total) return;
+  const int chunks_per_row = K / 8;
+  const int ch = idx % chunks_per_row;
+  long long t = idx / chunks_per_row;
+  const int r = t % R_pad;
+  const int g = t / R_pad;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (r < R) v = *reinterpret_cast<const uint4*>(src + ((long long)g * R + r) * K + ch * 8);
+  const int kc = ch >> 3, c = ch & 7;
+  const int num_kc = K / 64;
+  __half* d = dst + (((long long)g * num_kc + kc) * R_pad + r) * 64 + ((c ^ (r & 7)) << 3);
+  *reinterpret_cast<uint4*>(d) = v;
+}
+
+// 2x2 average pooling of every [h][w] correlation map (F.avg_pool2d(corr, 2, stride=2), corr.py:25-27).
+__global__ void corr_pool(const __half* __restrict__ src, __half* __restrict__ dst, long long nq, int h, int w) {
+  const int oh = h >> 1, ow = w >> 1;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= nq * oh * ow) return;
+  const int ox = idx % ow;
+  long long t = idx / ow;
+  const int oy = t % oh;
+  const long long q = t / oh;
+  const __half* s = src + (q * h + 2 * oy) * w + 2 * ox;
+  const float a = __half2float(s[0]) + __half2float(s[1]) + __half2float(s[w]) + __half2float(s[w + 1]);
+  dst[idx] = __float2half_rn(0.25f * a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Correlation lookup (CorrBlock.__call__, corr.py:29-50; bilinear_sampler, RAFT/utils/utils.py:66-80).
+// Output channel c = l*81 + i*9 + j samples level l at (x/2^l + (i-4), y/2^l + (j-4)), bilinear,
+// zeros outside, align_corners=True.  One thread per output channel: consecutive threads write
+// consecutive channels (coalesced 2-byte stores); the 10x10 tap window of a query pixel is shared by
+// its 81 threads per level through L1.
+// ------------------------------------------------------------------------------------------------
+struct CorrLevels {
+  const __half* p[4];
+};
+
+__global__ void corr_lookup(CorrLevels lv, const float* __restrict__ coords, __half* __restrict__ out, int out_cs,
+                            long long nq, int P, int h8, int w8) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= nq * out_cs) return;
+  const int c = idx % out_cs;
+  const long long q = idx / out_cs;
+  if (c >= 324) { out[idx] = __float2half_rn(0.f); return; }
+  const int l = c / 81, r = c - l * 81;
+  const int i = r / 9, j = r - i * 9;
+  const float cx = coords[q * 2], cy = coords[q * 2 + 1];
+  const float inv = 1.f / (float)(1 << l);
+  const int h = h8 >> l, w = w8 >> l;
+  // the reference normalises to [-1,1] and grid_sample maps back; both are exact inverses up to fp32 rounding
+  const float x = cx * inv + (float)(i - 4), y = cy * inv + (float)(j - 4);
+  const float fx = floorf(x), fy = floorf(y);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float ax = x - fx, ay = y - fy;
+  const __half* m = lv.p[l] + q * (long long)(h * w);
+  float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+  const bool xin0 = x0 >= 0 && x0 < w, xin1 = x0 + 1 >= 0 && x0 + 1 < w;
+  const bool yin0 = y0 >= 0 && y0 < h, yin1 = y0 + 1 >= 0 && y0 + 1 < h;
+  if (yin0 && xin0) v00 = __half2float(m[y0 * w + x0]);
+  if (yin0 && xin1) v01 = __half2float(m[y0 * w + x0 + 1]);
+  if (yin1 && xin0) v10 = __half2float(m[(y0 + 1) * w + x0]);
+  if (yin1 && xin1) v11 = __half2float(m[(y0 + 1) * w + x0 + 1]);
+  const float val = (1.f - ay) * ((1.f - ax) * v00 + ax * v01) + ay * ((1.f - ax) * v10 + ax * v11);
+  out[idx] = __float2half_rn(val);
+}
+
+// cnet output -> GRU state: h = tanh(c[:, :128]) into hx[:, 0:128], inp = relu(c[:, 128:]) into hx[:, 128:256]
+// (raft.py:119-122)
+__global__ void cnet_split(const __half* __restrict__ c, __half* __restrict__ hx, int hx_cs, long long total) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ch = idx % 256;
+  const long long p = idx / 256;
+  const float v = __half2float(c[idx]);
+  hx[p * hx_cs + ch] = __float2half_rn(ch < 128 ? tanhf(v) : fmaxf(v, 0.f));
+}
+
+// coords1 = coords0 (+ delta); flow = coords1 - coords0 written (fp16) to the motion-encoder input
+// ([.,8], channels 2..7 zero) and to the last two channels of the GRU input (raft.py:124-140).
+__global__ void raft_coords(const float* __restrict__ delta, float* __restrict__ coords1, __half* __restrict__ flow8,
+                            __half* __restrict__ hx, int hx_cs, int hx_flow_co, long long total, int P, int w8,
+                            int init) {
+  long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  const int p = q % P;
+  const float x0 = (float)(p % w8), y0 = (float)(p / w8);
+  float x, y;
+  if (init) { x = x0; y = y0; }
+  else { x = coords1[2 * q] + delta[2 * q]; y = coords1[2 * q + 1] + delta[2 * q + 1]; }
+  coords1[2 * q] = x;
+  coords1[2 * q + 1] = y;
+  const __half fx = __float2half_rn(x - x0), fy = __float2half_rn(y - y0);
+  __half* f = flow8 + q * 8;
+  f[0] = fx; f[1] = fy;
+  if (init) for (int k = 2; k < 8; ++k) f[k] = __float2half_rn(0.f);
+  hx[q * hx_cs + hx_flow_co] = fx;
+  hx[q * hx_cs + hx_flow_co + 1] = fy;
+}
+
+// Convex 8x upsampling (RAFT.upsample_flow, raft.py:81-92): softmax over the 9 neighbours' logits
+// mask[k*64 + sy*8 + sx], weighted sum of 8*flow (3x3 unfold, zero padding).  Output NCHW fp32.
+__global__ void convex_upsample(const float* __restrict__ coords1, const __half* __restrict__ mask,
+                                float* __restrict__ out, int B, int h8, int w8) {
+  const int H = 8 * h8, W = 8 * w8;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W) return;
+  const int X = idx % W;
+  long long t = idx / W;
+  const int Y = t % H;
+  const int b = t / H;
+  const int x = X >> 3, sx = X & 7, y = Y >> 3, sy = Y & 7;
+  const long long q = ((long long)b * h8 + y) * w8 + x;
+  const __half* mk = mask + q * 576 + sy * 8 + sx;
+  float lg[9], mx = -1e30f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { lg[k] = __half2float(mk[k * 64]); mx = fmaxf(mx, lg[k]); }
+  float den = 0.f, ux = 0.f, uy = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float e = __expf(lg[k] - mx);
+    den += e;
+    const int ny = y + k / 3 - 1, nx = x + k % 3 - 1;
+    if (ny >= 0 && ny < h8 && nx >= 0 && nx < w8) {
+      const long long nq = ((long long)b * h8 + ny) * w8 + nx;
+      ux += e * 8.f * (coords1[2 * nq] - (float)nx);
+      uy += e * 8.f * (coords1[2 * nq + 1] - (float)ny);
+    }
+  }
+  const long long HWl = (long long)H * W;
+  out[((long long)b * 2) * HWl + (long long)Y * W + X] = ux / den;
+  out[((long long)b * 2 + 1) * HWl + (long long)Y * W + X] = uy / den;
+}
+
+}  // namespace
+
+int pp_k_instnorm_stats(const __half* x, int N, int HW, int C, float* sums, cudaStream_t st) {
+  PP_REQUIRE(C % 2 == 0 && C <= 512, "instnorm: unsupported C=%d", C);
+  PP_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)N * 2 * C * sizeof(float), st));
+  const int pix_per_block = 1024;
+  dim3 grid(pp_ceil_div(HW, pix_per_block), N);
+  instnorm_stats<<<grid, 256, 2 * C * sizeof(float), st>>>(x, HW, C, sums, pix_per_block);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_instnorm_apply(const __half* x, const float* sums, const __half* residual, __half* out, int N, int HW, int C,
+                        int relu, cudaStream_t st) {
+  const long long total2 = (long long)N * HW * (C / 2);
+  instnorm_apply<<<nblocks(total2), TPB, 0, st>>>(x, sums, residual, out, HW, C, total2, relu);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_pack_b_operand(const __half* src, __half* dst, int G, int R, int R_pad, int K, cudaStream_t st) {
+  PP_REQUIRE(K % 64 == 0 && R_pad % 8 == 0, "pack_b_operand: K=%d must be a multiple of 64", K);
+  const long long total = (long long)G * R_pad * (K / 8);
+  pack_b_operand<<<nblocks(total), TPB, 0, st>>>(src, dst, R, R_pad, K, total);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_corr_pool(const __half* src, __half* dst, long long nq, int h, int w, cudaStream_t st) {
+  const long long total = nq * (h / 2) * (w / 2);
+  if (total == 0) return PP_OK;
+  corr_pool<<<nblocks(total), TPB, 0, st>>>(src, dst, nq, h, w);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_corr_lookup(const __half* l0, const __half* l1, const __half* l2, const __half* l3, const float* coords,
+                     __half* out, int out_cs, long long nq, int P, int h8, int w8, cudaStream_t st) {
+  PP_REQUIRE(out_cs >= 324, "corr_lookup: out_cs=%d < 324", out_cs);
+  CorrLevels lv;
+  lv.p[0] = l0; lv.p[1] = l1; lv.p[2] = l2; lv.p[3] = l3;
+  const long long total = nq * out_cs;
+  corr_lookup<<<nblocks(total), TPB, 0, st>>>(lv, coords, out, out_cs, nq, P, h8, w8);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_cnet_split(const __half* c, __half* hx, int hx_cs, long long npix, cudaStream_t st) {
+  cnet_split<<<nblocks(npix * 256), TPB, 0, st>>>(c, hx, hx_cs, npix * 256);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_raft_coords_init(float* coords1, __half* flow8, __half* hx, int hx_cs, int hx_flow_co, int B, int h8, int w8,
+                          cudaStream_t st) {
+  const long long total = (long long)B * h8 * w8;
+  raft_coords<<<nblocks(total), TPB, 0, st>>>(nullptr, coords1, flow8, hx, hx_cs, hx_flow_co, total, h8 * w8, w8, 1);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_raft_coords_update(const float* delta, float* coords1, __half* flow8, __half* hx, int hx_cs, int hx_flow_co,
+                            int B, int h8, int w8, cudaStream_t st) {
+  const long long total = (long long)B * h8 * w8;
+  raft_coords<<<nblocks(total), TPB, 0, st>>>(delta, coords1, flow8, hx, hx_cs, hx_flow_co, total, h8 * w8, w8, 0);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_convex_upsample(const float* coords1, const __half* mask, float* out_nchw, int B, int h8, int w8,
+                         cudaStream_t st) {
+  const long long total = (long long)B * 64 * h8 * w8;
+  convex_upsample<<<nblocks(total), TPB, 0, st>>>(coords1, mask, out_nchw, B, h8, w8);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}

@@ -1,0 +1,229 @@
+// Sparse-transformer support kernels: LayerNorm, pooled tokens, window flags, fold (overlap-add),
+// max-pool of masks, host-composite replacement.  The windowed attention itself is in attention.cu.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblocks(long long n, int per = TPB) { return (int)((n + per - 1) / per); }
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over C=512 (nn.LayerNorm, eps 1e-5; sparse_transformer.py:425-431).  One warp per token.
+// Rows are re-mapped from the [t][gh][gw] token grid into the zero-padded [t][nh][nw] grid the window
+// attention works on (padding tokens stay zero *before* the Q/K/V linears, sparse_transformer.py:212-221).
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm512(const __half* __restrict__ x, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, __half* __restrict__ out, long long rows, int gh, int gw,
+                             int nh, int nw) {
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + row * 512) + lane * 2;
+  uint4 raw[2] = {xp[0], xp[1]};
+  float v[16];
+  const __half2* h = reinterpret_cast<const __half2*>(raw);
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    s += f.x + f.y;
+    q += f.x * f.x + f.y * f.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const float mean = s * (1.f / 512.f);
+  const float var = fmaxf(q * (1.f / 512.f) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  __align__(16) __half2 o2[8];
+  const int c0 = lane * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = (v[2 * i] - mean) * rstd * gamma[c0 + 2 * i] + beta[c0 + 2 * i];
+    const float b = (v[2 * i + 1] - mean) * rstd * gamma[c0 + 2 * i + 1] + beta[c0 + 2 * i + 1];
+    o2[i] = __floats2half2_rn(a, b);
+  }
+  long long orow = row;
+  if (nh != gh || nw != gw) {
+    const int xx = row % gw;
+    const long long t = row / gw;
+    const int yy = t % gh;
+    const long long f = t / gh;
+    orow = (f * nh + yy) * nw + xx;
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + orow * 512) + lane * 2;
+  op[0] = reinterpret_cast<uint4*>(o2)[0];
+  op[1] = reinterpret_cast<uint4*>(o2)[1];
+}
+
+// Learned depthwise 4x4 stride-4 pooling of the (padded, normalised) tokens (pool_layer,
+// sparse_transformer.py:176-180, 294-297).  x [t][nh][nw][C] -> out [t][ph][pw][C]; w [C][16] fp32.
+__global__ void pool_tokens(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                            __half* __restrict__ out, int t, int nh, int nw, int ph, int pw, int C) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)t * ph * pw * C) return;
+  const int c = idx % C;
+  long long r = idx / C;
+  const int px = r % pw;
+  r /= pw;
+  const int py = r % ph;
+  const int f = r / ph;
+  float acc = b[c];
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx)
+      acc += w[c * 16 + ky * 4 + kx] *
+             __half2float(x[(((long long)f * nh + 4 * py + ky) * nw + 4 * px + kx) * C + c]);
+  out[idx] = __float2half_rn(acc);
+}
+
+// Window dispatch flags (propainter.py:417-428 max_pool(7,3,3) of the 1/4-res local masks, then
+// sparse_transformer.py:322-326 max over each 5x9 window and sum over local frames):
+// flag[w] = 1 if any local-frame mask pixel falls in the receptive field of any token of window w.
+// mask4: [lt][h4][w4] fp16 values at element stride cs (channel co).  One block per window.
+__global__ void window_flags(const __half* __restrict__ mask4, int cs, int co, int lt, int h4, int w4, int gh, int gw,
+                             int nww, int* __restrict__ flags) {
+  const int win = blockIdx.x;
+  const int wy = win / nww, wx = win % nww;
+  int any = 0;
+  const int per_frame = 5 * 9 * 49;
+  for (int i = threadIdx.x; i < lt * per_frame; i += blockDim.x) {
+    const int f = i / per_frame;
+    int r = i - f * per_frame;
+    const int tok = r / 49, tap = r - tok * 49;
+    const int ty = wy * 5 + tok / 9, tx = wx * 9 + tok % 9;
+    if (ty >= gh || tx >= gw) continue;  // zero padding of the mask grid
+    const int y = ty * 3 - 3 + tap / 7, x = tx * 3 - 3 + tap % 7;
+    if (y < 0 || y >= h4 || x < 0 || x >= w4) continue;
+    if (__half2float(mask4[(((long long)f * h4 + y) * w4 + x) * cs + co]) > 0.f) any = 1;
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) flags[win] = any;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Overlap-add of 7x7 stride-3 pad-3 patches (F.fold) in gather form, optionally divided by the overlap
+// count (FusionFeedForward, sparse_transformer.py:92-121) and passed through GELU (the reference applies
+// GELU after unfold; unfold only copies, and GELU(0)=0 keeps the zero padding, so GELU-then-unfold is
+// identical).  x: [t*gh*gw][cs], column (ky*7+kx)*C + c  (weights are permuted to this order when packed).
+// out: [t][H][W][C].  One thread per (pixel, 8-channel vector).
+// ------------------------------------------------------------------------------------------------
+__global__ void fold7x7s3(const __half* __restrict__ x, int cs, __half* __restrict__ out, int t, int H, int W, int C,
+                          int gh, int gw, int normalise, int gelu) {
+  const int C8 = C / 8;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)t * H * W * C8) return;
+  const int c8 = idx % C8;
+  long long p = idx / C8;
+  const int px = p % W;
+  p /= W;
+  const int py = p % H;
+  const int f = p / H;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  int cnt = 0;
+  const int ty1 = min((py + 3) / 3, gh - 1), tx1 = min((px + 3) / 3, gw - 1);
+  for (int ty = ty1; ty >= 0; --ty) {
+    const int ky = py + 3 - 3 * ty;
+    if (ky > 6) break;
+    for (int tx = tx1; tx >= 0; --tx) {
+      const int kx = px + 3 - 3 * tx;
+      if (kx > 6) break;
+      const uint4 q = *reinterpret_cast<const uint4*>(x + (((long long)f * gh + ty) * gw + tx) * cs +
+                                                      (ky * 7 + kx) * C + c8 * 8);
+      const __half2* hq = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 v = __half22float2(hq[e]);
+        acc[2 * e] += v.x;
+        acc[2 * e + 1] += v.y;
+      }
+      ++cnt;
+    }
+  }
+  const float inv = (normalise && cnt > 0) ? 1.f / (float)cnt : 1.f;
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float a = acc[2 * e] * inv, b = acc[2 * e + 1] * inv;
+    if (gelu) { a = ppx::gelu_erf(a); b = ppx::gelu_erf(b); }
+    o[e] = __floats2half2_rn(a, b);
+  }
+  *reinterpret_cast<uint4*>(out + ((((long long)f * H + py) * W + px) * C) + c8 * 8) = *reinterpret_cast<uint4*>(o);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device replacement of the host composite (propainter_inference.py:283-307) with identical integer
+// semantics: img = trunc((pred+1)/2*255); sel = img*m + orig*(1-m) in uint8; first visit stores, later
+// visits store trunc(0.5*prev + 0.5*sel).  `visited[frame]` is updated by the host between launches.
+// ------------------------------------------------------------------------------------------------
+__global__ void composite(const __half* __restrict__ pred, int pred_cs, const float* __restrict__ masks,
+                          const uint8_t* __restrict__ orig, uint8_t* __restrict__ comp,
+                          const int* __restrict__ frame_ids, const int* __restrict__ first_visit, int lt,
+                          long long HW) {
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)lt * HW) return;
+  const int i = idx / HW;
+  const long long p = idx - (long long)i * HW;
+  const int fr = frame_ids[i];
+  const int m = (int)(uint8_t)masks[(long long)fr * HW + p];
+  const __half* pr = pred + idx * pred_cs;
+  const uint8_t* og = orig + ((long long)fr * HW + p) * 3;
+  uint8_t* cp = comp + ((long long)fr * HW + p) * 3;
+  const int first = first_visit[i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = (__half2float(pr[c]) + 1.f) / 2.f * 255.f;
+    const uint8_t pu = (uint8_t)(int)v;  // astype(np.uint8): truncation (values are within [0,255])
+    const uint8_t sel = (uint8_t)(pu * m + og[c] * (1 - m));
+    cp[c] = first ? sel : (uint8_t)(int)((float)cp[c] * 0.5f + (float)sel * 0.5f);
+  }
+}
+
+}  // namespace
+
+int pp_k_layernorm(const __half* x, const float* gamma, const float* beta, __half* out, long long rows, int gh, int gw,
+                   int nh, int nw, cudaStream_t st) {
+  if (rows == 0) return PP_OK;
+  layernorm512<<<nblocks(rows * 32), TPB, 0, st>>>(x, gamma, beta, out, rows, gh, gw, nh, nw);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_pool_tokens(const __half* x, const float* w, const float* b, __half* out, int t, int nh, int nw, int ph,
+                     int pw, int C, cudaStream_t st) {
+  const long long total = (long long)t * ph * pw * C;
+  if (total == 0) return PP_OK;
+  pool_tokens<<<nblocks(total), TPB, 0, st>>>(x, w, b, out, t, nh, nw, ph, pw, C);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_window_flags(const __half* mask4, int cs, int co, int lt, int h4, int w4, int gh, int gw, int nwh, int nww,
+                      int* flags, cudaStream_t st) {
+  window_flags<<<nwh * nww, 256, 0, st>>>(mask4, cs, co, lt, h4, w4, gh, gw, nww, flags);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_fold(const __half* x, int cs, __half* out, int t, int H, int W, int C, int gh, int gw, int normalise,
+              int gelu, cudaStream_t st) {
+  PP_REQUIRE(C % 8 == 0 && cs % 8 == 0, "fold: C=%d cs=%d must be multiples of 8", C, cs);
+  const long long total = (long long)t * H * W * (C / 8);
+  fold7x7s3<<<nblocks(total), TPB, 0, st>>>(x, cs, out, t, H, W, C, gh, gw, normalise, gelu);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_composite(const __half* pred, int pred_cs, const float* masks, const uint8_t* orig, uint8_t* comp,
+                   const int* frame_ids, const int* first_visit, int lt, int H, int W, cudaStream_t st) {
+  const long long HW = (long long)H * W;
+  composite<<<nblocks(HW * lt), TPB, 0, st>>>(pred, pred_cs, masks, orig, comp, frame_ids, first_visit, lt, HW);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}

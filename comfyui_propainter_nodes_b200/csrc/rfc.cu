@@ -1,0 +1,195 @@
+// Stage 2: recurrent flow completion (reference: model/recurrent_flow_completion.py:315-400,
+// propainter_inference.py:102-156).  forward_bidirect_flow runs the same network on the forward flows and on
+// the time-flipped backward flows; the two passes are independent, so they are batched here (D = 2 clips),
+// which halves the number of serial propagation steps.
+//
+// Frame order in every buffer is time-major: image index n = t*D + d.  A time slice is then D contiguous
+// images (what the propagation convs need), and the (3,1,1) dilation-2 temporal convs of the P3D blocks
+// become 2-D convs with kernel (3,1) over an "image" of height Tn and width D*h*w.
+#include <string.h>
+
+#include "engine.cuh"
+
+namespace {
+
+constexpr int D = 2;
+
+// P3DBlock (:162-205) followed by the Sequential's LeakyReLU(0.2): spatial 3x3 (stride s) + LReLU, then
+// temporal (3,1,1) dilation 2 + LReLU.
+int p3d(PPEngine& e, const std::string& name, const __half* x, int Tn, int H, int W, int Cin, int stride, int Cout,
+        __half* tmp, __half* out, cudaStream_t st) {
+  const int oh = (H + 2 - 3) / stride + 1, ow = (W + 2 - 3) / stride + 1;
+  PP_TRY(PPConvCall(e, name + ".conv1", Tn * D, H, W).in(x, Cin, 0, Cin).geom(stride, stride, 1, 1)
+             .out(tmp, Cout, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(PPConvCall(e, name + ".conv2", 1, Tn, D * oh * ow).in(tmp, Cout, 0, Cout).geom(1, 1, 2, 0, 2, 1)
+             .out(out, Cout, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+  return PP_OK;
+}
+
+}  // namespace
+
+int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows_b, const float* flow_masks, int T,
+                           int H, int W, float* out_f, float* out_b, cudaStream_t st) {
+  PP_REQUIRE(T >= 2, "flow completion: need at least 2 frames");
+  PP_REQUIRE(H % 8 == 0 && W % 8 == 0, "flow completion: size %dx%d must be a multiple of 8", W, H);
+  const int Tn = T - 1, N = Tn * D;
+  const int h2 = H / 2, w2 = W / 2, h4 = H / 4, w4 = W / 4, h8 = H / 8, w8 = W / 8, P = h8 * w8;
+  const long long HW = (long long)H * W;
+  const size_t mark0 = e.arena.mark();
+
+  // ---- input: cat(flow*(1-m), m); forward flows use masks[:-1], backward flows masks[1:] and flipped time
+  __half* x8;
+  PP_TRY(pp_alloc(e, &x8, (size_t)N * HW * 8, "rfc input"));
+  PP_TRY(pp_k_rfc_pack_input(flows_f, flow_masks, x8, D * HW, Tn, H, W, 0, st));
+  PP_TRY(pp_k_rfc_pack_input(flows_b, flow_masks + HW, x8 + HW * 8, D * HW, Tn, H, W, 1, st));
+  e.launches += 2;
+
+  // ---- encoder ---------------------------------------------------------------------------------
+  __half *x, *t1, *e1a, *e1, *e2a, *e2;
+  PP_TRY(pp_alloc(e, &x, (size_t)N * h2 * w2 * 32, "rfc x"));
+  PP_TRY(pp_alloc(e, &t1, (size_t)N * h2 * w2 * 32, "rfc tmp"));
+  PP_TRY(pp_alloc(e, &e1a, (size_t)N * h2 * w2 * 32, "rfc e1a"));
+  PP_TRY(pp_alloc(e, &e1, (size_t)N * h4 * w4 * 64, "rfc e1"));
+  PP_TRY(pp_alloc(e, &e2a, (size_t)N * h4 * w4 * 64, "rfc e2a"));
+  PP_TRY(pp_alloc(e, &e2, (size_t)N * P * 128, "rfc e2"));
+  PP_TRY(PPConvCall(e, "rfc.downsample", N, H, W).in(x8, 8, 0, 8).geom(2, 2, 2, 2, 1, 1, 1)
+             .out(x, 32, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(p3d(e, "rfc.encoder1.0", x, Tn, h2, w2, 32, 1, 32, t1, e1a, st));
+  PP_TRY(p3d(e, "rfc.encoder1.2", e1a, Tn, h2, w2, 32, 2, 64, t1, e1, st));
+  PP_TRY(p3d(e, "rfc.encoder2.0", e1, Tn, h4, w4, 64, 1, 64, t1, e2a, st));
+  PP_TRY(p3d(e, "rfc.encoder2.2", e2a, Tn, h4, w4, 64, 2, 128, t1, e2, st));
+  // mid_dilation: three (1,3,3) convs with dilation 3, 2, 1 (:266-280)
+  __half *mid, *mid2;
+  PP_TRY(pp_alloc(e, &mid, (size_t)N * P * 128, "rfc mid"));
+  PP_TRY(pp_alloc(e, &mid2, (size_t)N * P * 128, "rfc mid2"));
+  PP_TRY(PPConvCall(e, "rfc.mid.0", N, h8, w8).in(e2, 128, 0, 128).geom(1, 1, 3, 3, 3, 3).out(mid, 128, 0)
+             .act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(PPConvCall(e, "rfc.mid.1", N, h8, w8).in(mid, 128, 0, 128).geom(1, 1, 2, 2, 2, 2).out(mid2, 128, 0)
+             .act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(PPConvCall(e, "rfc.mid.2", N, h8, w8).in(mid2, 128, 0, 128).geom(1, 1, 1, 1, 1, 1).out(mid, 128, 0)
+             .act(PP_ACT_LRELU, 0.2f).run(st));
+
+  // ---- bidirectional second-order deformable propagation (:77-143) -------------------------------
+  const size_t slice = (size_t)D * P * 128;  // elements of one time slice
+  __half *fb, *ff, *zero, *o1, *o2, *offs, *cols, *aligned, *bb;
+  PP_TRY(pp_alloc(e, &fb, (size_t)Tn * slice, "rfc feats backward"));
+  PP_TRY(pp_alloc(e, &ff, (size_t)Tn * slice, "rfc feats forward"));
+  PP_TRY(pp_alloc(e, &zero, slice, "rfc zeros"));
+  PP_TRY(pp_alloc(e, &o1, slice, "rfc o1"));
+  PP_TRY(pp_alloc(e, &o2, slice, "rfc o2"));
+  PP_TRY(pp_alloc(e, &offs, (size_t)D * P * 432, "rfc offsets"));
+  PP_TRY(pp_alloc(e, &cols, (size_t)D * P * 2304, "rfc dcn columns"));
+  PP_TRY(pp_alloc(e, &aligned, slice, "rfc aligned"));
+  PP_TRY(pp_alloc(e, &bb, slice, "rfc backbone tmp"));
+  PP_CUDA_CHECK(cudaMemsetAsync(zero, 0, slice * sizeof(__half), st));
+  for (int mod = 0; mod < 2; ++mod) {
+    const std::string m = mod == 0 ? "rfc.fp.backward_" : "rfc.fp.forward_";
+    __half* feats = mod == 0 ? fb : ff;
+    for (int i = 0; i < Tn; ++i) {
+      const int idx = mod == 0 ? Tn - 1 - i : i;
+      const int prev = mod == 0 ? idx + 1 : idx - 1, prev2 = mod == 0 ? idx + 2 : idx - 2;
+      const __half* cur = mid + (size_t)idx * slice;
+      const __half* prop = zero;
+      if (i > 0) {
+        const __half* p1 = feats + (size_t)prev * slice;
+        const __half* n2 = i > 1 ? feats + (size_t)prev2 * slice : zero;
+        // cond = cat(prop, cur, n2) -> 4-conv offset head (:17-26, 32-42)
+        PP_TRY(PPConvCall(e, m + ".offset.0", D, h8, w8).in(p1, 128, 0, 128).in(cur, 128, 0, 128).in(n2, 128, 0, 128)
+                   .out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
+        PP_TRY(PPConvCall(e, m + ".offset.1", D, h8, w8).in(o1, 128, 0, 128).out(o2, 128, 0)
+                   .act(PP_ACT_LRELU, 0.1f).run(st));
+        PP_TRY(PPConvCall(e, m + ".offset.2", D, h8, w8).in(o2, 128, 0, 128).out(o1, 128, 0)
+                   .act(PP_ACT_LRELU, 0.1f).run(st));
+        PP_TRY(PPConvCall(e, m + ".offset.3", D, h8, w8).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
+        // modulated deformable conv on cat(prop, n2): sample -> GEMM (K = 9*256)
+        PP_TRY(pp_k_dcn_sample(p1, 128, 0, 128, n2, 128, 0, 128, offs, 432, nullptr, 0, 0, 5.0f, cols, D, h8, w8, st));
+        e.launches++;
+        PP_TRY(PPConvCall(e, m + ".dcn", D, h8, w8).in(cols, 2304, 0, 2304).geom(1, 1, 0, 0).out(aligned, 128, 0)
+                   .run(st));
+        prop = aligned;
+      }
+      // feat_prop = feat_prop + backbone(cat(cur, [backward feature of this frame], feat_prop))
+      PPConvCall b0(e, m + ".backbone.0", D, h8, w8);
+      b0.in(cur, 128, 0, 128);
+      if (mod == 1) b0.in(fb + (size_t)idx * slice, 128, 0, 128);
+      b0.in(prop, 128, 0, 128).out(bb, 128, 0).act(PP_ACT_LRELU, 0.1f);
+      PP_TRY(b0.run(st));
+      PP_TRY(PPConvCall(e, m + ".backbone.1", D, h8, w8).in(bb, 128, 0, 128).out(feats + (size_t)idx * slice, 128, 0)
+                 .residual(prop, 128, 0).run(st));
+    }
+  }
+  // fusion(cat(backward, forward)) + x  (:138-143)
+  __half* fused = e2;  // e2 is dead
+  PP_TRY(PPConvCall(e, "rfc.fp.fusion", N, h8, w8).in(fb, 128, 0, 128).in(ff, 128, 0, 128).geom(1, 1, 0, 0)
+             .out(fused, 128, 0).residual(mid, 128, 0).run(st));
+
+  // ---- decoders (:282-300, 333-345); deconv = bilinear x2 (align_corners) + 3x3 conv ----------------
+  __half *d2a, *up, *d2, *d1a, *d1, *u0, *pred;
+  PP_TRY(pp_alloc(e, &d2a, (size_t)N * P * 128, "rfc d2a"));
+  PP_TRY(pp_alloc(e, &up, (size_t)N * HW * 32, "rfc upsampled"));
+  PP_TRY(pp_alloc(e, &d2, (size_t)N * h4 * w4 * 64, "rfc d2"));
+  PP_TRY(pp_alloc(e, &d1a, (size_t)N * h4 * w4 * 64, "rfc d1a"));
+  PP_TRY(pp_alloc(e, &d1, (size_t)N * h2 * w2 * 32, "rfc d1"));
+  PP_TRY(pp_alloc(e, &u0, (size_t)N * h2 * w2 * 32, "rfc u0"));
+  PP_TRY(pp_alloc(e, &pred, (size_t)N * HW * 2, "rfc pred"));
+  PP_TRY(PPConvCall(e, "rfc.decoder2.0", N, h8, w8).in(fused, 128, 0, 128).out(d2a, 128, 0)
+             .act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(pp_k_upsample2x(d2a, 128, 0, up, 128, 0, N, h8, w8, 128, st));
+  PP_TRY(PPConvCall(e, "rfc.decoder2.deconv", N, h4, w4).in(up, 128, 0, 128).out(d2, 64, 0)
+             .act(PP_ACT_LRELU, 0.2f).residual(e1, 64, 0).run(st));
+  PP_TRY(PPConvCall(e, "rfc.decoder1.0", N, h4, w4).in(d2, 64, 0, 64).out(d1a, 64, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(pp_k_upsample2x(d1a, 64, 0, up, 64, 0, N, h4, w4, 64, st));
+  PP_TRY(PPConvCall(e, "rfc.decoder1.deconv", N, h2, w2).in(up, 64, 0, 64).out(d1, 32, 0)
+             .act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(PPConvCall(e, "rfc.upsample.0", N, h2, w2).in(d1, 32, 0, 32).out(u0, 32, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+  PP_TRY(pp_k_upsample2x(u0, 32, 0, up, 32, 0, N, h2, w2, 32, st));
+  PP_TRY(PPConvCall(e, "rfc.upsample.deconv", N, H, W).in(up, 32, 0, 32).out(pred, 2, 0).run(st));
+  e.launches += 3;
+
+  // ---- combine_flow (:389-400) and un-flip ----------------------------------------------------------
+  PP_TRY(pp_k_rfc_combine(pred, 2, D * HW, flows_f, flow_masks, out_f, Tn, H, W, 0, st));
+  PP_TRY(pp_k_rfc_combine(pred + HW * 2, 2, D * HW, flows_b, flow_masks + HW, out_b, Tn, H, W, 1, st));
+  e.launches += 2;
+  e.arena.release(mark0);
+  return PP_OK;
+}
+
+// Stage 3a: non-learnable image propagation (reference: propainter_inference.py:159-225 single-chunk branch,
+// model/propainter.py:118-231 with learnable=False).  One fused kernel per time step.
+int pp_stage_image_propagate(PPEngine& e, const float* frames, const float* masks, const float* flows_f,
+                             const float* flows_b, int T, int H, int W, float* upd_frames, float* upd_masks,
+                             cudaStream_t st) {
+  PP_REQUIRE(T >= 2, "image propagation: need at least 2 frames");
+  const long long HW = (long long)H * W;
+  const size_t mark0 = e.arena.mark();
+  __half *in4, *bwd, *fwd, *ff, *fbk;
+  PP_TRY(pp_alloc(e, &in4, (size_t)T * HW * 4, "imgprop input"));
+  PP_TRY(pp_alloc(e, &bwd, (size_t)T * HW * 4, "imgprop backward"));
+  PP_TRY(pp_alloc(e, &fwd, (size_t)T * HW * 4, "imgprop forward"));
+  PP_TRY(pp_alloc(e, &ff, (size_t)(T - 1) * HW * 2, "imgprop flows f"));
+  PP_TRY(pp_alloc(e, &fbk, (size_t)(T - 1) * HW * 2, "imgprop flows b"));
+  PP_TRY(pp_k_imgprop_pack(frames, masks, in4, T, H, W, st));
+  PP_TRY(pp_k_flow_to_nhwc2(flows_f, ff, T - 1, H, W, st));
+  PP_TRY(pp_k_flow_to_nhwc2(flows_b, fbk, T - 1, H, W, st));
+  e.launches += 3;
+  const size_t fs = (size_t)HW * 4, ws = (size_t)HW * 2;
+  // backward pass: idx = T-1..0, prop flow = flows_forward[idx], check flow = flows_backward[idx]
+  PP_CUDA_CHECK(cudaMemcpyAsync(bwd + (size_t)(T - 1) * fs, in4 + (size_t)(T - 1) * fs, fs * sizeof(__half),
+                                cudaMemcpyDeviceToDevice, st));
+  for (int idx = T - 2; idx >= 0; --idx) {
+    PP_TRY(pp_k_imgprop_step(in4 + idx * fs, bwd + (idx + 1) * fs, bwd + idx * fs, ff + idx * ws, fbk + idx * ws, H, W,
+                             st));
+    e.launches++;
+  }
+  // forward pass over the backward pass's outputs: prop flow = flows_backward[idx-1], check = flows_forward[idx-1]
+  PP_CUDA_CHECK(cudaMemcpyAsync(fwd, bwd, fs * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+  for (int idx = 1; idx < T; ++idx) {
+    PP_TRY(pp_k_imgprop_step(bwd + idx * fs, fwd + (idx - 1) * fs, fwd + idx * fs, fbk + (idx - 1) * ws,
+                             ff + (idx - 1) * ws, H, W, st));
+    e.launches++;
+  }
+  PP_TRY(pp_k_imgprop_finish(fwd, frames, masks, upd_frames, upd_masks, T, H, W, st));
+  e.launches++;
+  e.arena.release(mark0);
+  return PP_OK;
+}

@@ -1,0 +1,402 @@
+"""ctypes binding of libpropainter_b200.so + checkpoint packing for the sm_100a kernels.
+
+PyTorch is used here only for device memory, streams and host-side weight re-layout; every compute
+step goes through the C ABI declared in include/propainter_b200.h.  There is NO fallback path: if the
+shared library is missing or the device is not a B200, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Dict, Tuple
+
+import torch
+
+from . import weights as Wspec
+
+_LIB = None
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libpropainter_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH, ACT_GELU = range(6)
+
+_VP, _I, _F, _LL, _SZ, _CP = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t,
+                              ctypes.c_char_p)
+# name -> (restype, argtypes); must list every symbol declared in include/propainter_b200.h
+_SIGNATURES = {
+    "pp_last_error": (_CP, []),
+    "pp_version": (_CP, []),
+    "pp_create": (_I, [_I, _VP, _SZ, ctypes.POINTER(_VP)]),
+    "pp_destroy": (_I, [_VP]),
+    "pp_register_conv": (_I, [_VP, _CP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I]),
+    "pp_register_tensor": (_I, [_VP, _CP, _VP, _SZ]),
+    "pp_raft_bidir": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
+    "pp_flow_complete": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
+    "pp_image_propagate": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
+    "pp_gen_begin": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "pp_gen_window": (_I, [_VP, ctypes.POINTER(_I), _I, _I, _VP, _VP]),
+    "pp_gen_end": (_I, [_VP]),
+    "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "pp_launch_count": (_LL, [_VP]),
+    "pp_workspace_peak": (_SZ, [_VP]),
+    "pp_op_conv": (_I, [_VP, _CP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _F, _VP, _VP, _VP]),
+    "pp_op_corr_lookup": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _LL, _I, _I, _VP]),
+    "pp_op_imgprop_step": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP]),
+    "pp_op_attention": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
+}
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the CUDA library (built in-tree by ``__graft_entry__.build()`` / ``make -C csrc``)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_PKG_DIR, 'csrc')}` "
+                "(there is no CPU or PyTorch fallback for the ProPainter hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing (host side)
+# ----------------------------------------------------------------------------------------------
+
+
+def choose_bn(cout: int) -> Tuple[int, int]:
+    """N-tile of the tcgen05 GEMM: fewest tiles of <= 256 columns, each a multiple of 16."""
+    n_tiles = (cout + 255) // 256
+    bn = ((cout + n_tiles - 1) // n_tiles + 15) // 16 * 16
+    return bn, bn * n_tiles
+
+
+def pack_conv_weight(w: torch.Tensor, groups: int = 1, cin_map=None):
+    """[Cout, Cin_g, kh, kw] fp32 -> swizzled B-operand image + metadata.
+
+    K is ordered (ky, kx, ci) with ci running over the *kernel's* input channels: ``cin_map[ci]`` is
+    the reference input channel feeding kernel channel ci, or -1 for a zero (padding) channel.
+    Layout: [groups][K_pad/64][cout_g_pad] rows of 64 fp16; inside each 128-byte row the 16-byte chunk
+    c is stored at position c ^ (row & 7) (the 128B swizzle the UMMA descriptor expects)."""
+    w = w.detach().float().cpu()
+    cout, cin_ref, kh, kw = w.shape
+    if cin_map is None:
+        cin_map = list(range(cin_ref)) + [-1] * ((-cin_ref) % 8)
+    assert len(cin_map) % 8 == 0
+    cin_k = len(cin_map)
+    idx = torch.tensor([max(i, 0) for i in cin_map], dtype=torch.long)
+    keep = torch.tensor([1.0 if i >= 0 else 0.0 for i in cin_map])
+    wk = w[:, idx] * keep.view(1, -1, 1, 1)                # [Cout, cin_k, kh, kw]
+    wk = wk.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin_k)   # K = (ky, kx, ci)
+    cout_g = cout // groups
+    bn, cout_g_pad = choose_bn(cout_g)
+    K = wk.shape[1]
+    K_pad = (K + 63) // 64 * 64
+    buf = torch.zeros(groups, cout_g_pad, K_pad)
+    buf[:, :cout_g, :K] = wk.view(groups, cout_g, K)
+    num_kc = K_pad // 64
+    buf = buf.view(groups, cout_g_pad, num_kc, 8, 8).permute(0, 2, 1, 3, 4).contiguous()  # [G, kc, row, chunk, 8]
+    rows = torch.arange(cout_g_pad)
+    pos = torch.arange(8).view(1, 8) ^ (rows.view(-1, 1) & 7)                               # position p holds chunk p^(r&7)
+    buf = torch.gather(buf, 3, pos.view(1, 1, cout_g_pad, 8, 1).expand(groups, num_kc, cout_g_pad, 8, 8))
+    meta = dict(cout_g=cout_g, cout_g_pad=cout_g_pad, bn=bn, cin_g=cin_k, kh=kh, kw=kw, groups=groups)
+    return buf.to(torch.float16).contiguous(), meta
+
+
+def _fold_bn(w, b, sd, p, eps=1e-5):
+    scale = sd[p + ".weight"] / torch.sqrt(sd[p + ".running_var"] + eps)
+    return w * scale.view(-1, 1, 1, 1), (b - sd[p + ".running_mean"]) * scale + sd[p + ".bias"]
+
+
+def _pad_map(n_real: int, total: int):
+    return list(range(n_real)) + [-1] * (total - n_real)
+
+
+def build_layers(raft_sd, rfc_sd, gen_sd):
+    """-> (convs: name -> (weight[Cout,Cin,kh,kw], bias, groups, cin_map), tensors: name -> fp32 tensor)."""
+    convs: Dict[str, tuple] = {}
+    tens: Dict[str, torch.Tensor] = {}
+
+    def add(name, w, b, groups=1, cin_map=None):
+        convs[name] = (w.float(), None if b is None else b.float(), groups, cin_map)
+
+    # ------------------------------------------------------------------ RAFT
+    r = {(k[7:] if k.startswith("module.") else k): v.float() for k, v in raft_sd.items()}
+    Wspec.check_state_dict(r, Wspec.raft_spec())
+    for net, bn in (("fnet", False), ("cnet", True)):
+        def cv(dst, src, norm=None, cin_map=None):
+            w, b = r[f"{net}.{src}.weight"], r[f"{net}.{src}.bias"]
+            if bn and norm is not None:
+                w, b = _fold_bn(w, b, r, f"{net}.{norm}")
+            add(f"raft.{net}.{dst}", w, b, 1, cin_map)
+        cv("conv1", "conv1", "norm1", _pad_map(3, 8))
+        for li in (1, 2, 3):
+            for bi in (0, 1):
+                q = f"layer{li}.{bi}."
+                cv(q + "conv1", q + "conv1", q + "norm1")
+                cv(q + "conv2", q + "conv2", q + "norm2")
+                if li > 1 and bi == 0:
+                    cv(q + "downsample", q + "downsample.0", q + "norm3")
+        cv("conv2", "conv2")
+    u = "update_block."
+    add("raft.update.convc1", r[u + "encoder.convc1.weight"], r[u + "encoder.convc1.bias"], 1, _pad_map(324, 328))
+    add("raft.update.convc2", r[u + "encoder.convc2.weight"], r[u + "encoder.convc2.bias"])
+    add("raft.update.convf1", r[u + "encoder.convf1.weight"], r[u + "encoder.convf1.bias"], 1, _pad_map(2, 8))
+    add("raft.update.convf2", r[u + "encoder.convf2.weight"], r[u + "encoder.convf2.bias"])
+    add("raft.update.conv", r[u + "encoder.conv.weight"], r[u + "encoder.conv.bias"])
+    for s in ("1", "2"):
+        add("raft.update.gru.zr" + s, torch.cat([r[u + f"gru.convz{s}.weight"], r[u + f"gru.convr{s}.weight"]], 0),
+            torch.cat([r[u + f"gru.convz{s}.bias"], r[u + f"gru.convr{s}.bias"]], 0))
+        add("raft.update.gru.q" + s, r[u + f"gru.convq{s}.weight"], r[u + f"gru.convq{s}.bias"])
+    add("raft.update.fh1", r[u + "flow_head.conv1.weight"], r[u + "flow_head.conv1.bias"])
+    add("raft.update.fh2", r[u + "flow_head.conv2.weight"], r[u + "flow_head.conv2.bias"])
+    add("raft.update.mask0", r[u + "mask.0.weight"], r[u + "mask.0.bias"])
+    add("raft.update.mask2", r[u + "mask.2.weight"], r[u + "mask.2.bias"])
+
+    # ------------------------------------------------------------------ flow completion
+    f = {k: v.float() for k, v in rfc_sd.items()}
+    Wspec.check_state_dict(f, Wspec.rfc_spec())
+    add("rfc.downsample", f["downsample.0.weight"][:, :, 0], f["downsample.0.bias"], 1, _pad_map(3, 8))
+    for enc in ("encoder1", "encoder2"):
+        for i in (0, 2):
+            add(f"rfc.{enc}.{i}.conv1", f[f"{enc}.{i}.conv1.0.weight"][:, :, 0], f[f"{enc}.{i}.conv1.0.bias"])
+            add(f"rfc.{enc}.{i}.conv2", f[f"{enc}.{i}.conv2.0.weight"][:, :, :, :, 0], f[f"{enc}.{i}.conv2.0.bias"])
+    for j, i in enumerate((0, 2, 4)):
+        add(f"rfc.mid.{j}", f[f"mid_dilation.{i}.weight"][:, :, 0], f[f"mid_dilation.{i}.bias"])
+
+    def add_align(dst, sd, src):
+        for j, i in enumerate((0, 2, 4, 6)):
+            w = sd[f"{src}.conv_offset.{i}.weight"]
+            cm = None if w.shape[1] % 8 == 0 else _pad_map(w.shape[1], (w.shape[1] + 7) // 8 * 8)
+            add(f"{dst}.offset.{j}", w, sd[f"{src}.conv_offset.{i}.bias"], 1, cm)
+        w = sd[src + ".weight"]                                        # [Cout, Cin, 3, 3] -> K = (tap, ci)
+        add(f"{dst}.dcn", w.permute(0, 2, 3, 1).reshape(w.shape[0], -1, 1, 1), sd[src + ".bias"])
+
+    fp = "feat_prop_module."
+    for d in ("backward_", "forward_"):
+        add_align(f"rfc.fp.{d}", f, fp + "deform_align." + d)
+        add(f"rfc.fp.{d}.backbone.0", f[fp + f"backbone.{d}.0.weight"], f[fp + f"backbone.{d}.0.bias"])
+        add(f"rfc.fp.{d}.backbone.1", f[fp + f"backbone.{d}.2.weight"], f[fp + f"backbone.{d}.2.bias"])
+    add("rfc.fp.fusion", f[fp + "fusion.weight"], f[fp + "fusion.bias"])
+    for dst, src in (("decoder2.0", "decoder2.0"), ("decoder2.deconv", "decoder2.2.conv"), ("decoder1.0", "decoder1.0"),
+                     ("decoder1.deconv", "decoder1.2.conv"), ("upsample.0", "upsample.0"),
+                     ("upsample.deconv", "upsample.2.conv")):
+        add("rfc." + dst, f[src + ".weight"], f[src + ".bias"])
+
+    # ------------------------------------------------------------------ generator
+    g = {k: v.float() if v.is_floating_point() else v for k, v in gen_sd.items()}
+    Wspec.check_state_dict(g, Wspec.generator_spec())
+    enc_groups = {0: 1, 2: 1, 4: 1, 6: 1, 8: 1, 10: 2, 12: 4, 14: 8, 16: 1}
+    for i, gr in enc_groups.items():
+        add(f"gen.encoder.{i}", g[f"encoder.layers.{i}.weight"], g[f"encoder.layers.{i}.bias"], gr,
+            _pad_map(5, 8) if i == 0 else None)
+    for dst, src in (("0", "0.conv"), ("2", "2"), ("4", "4.conv"), ("6", "6")):
+        add("gen.decoder." + dst, g[f"decoder.{src}.weight"], g[f"decoder.{src}.bias"])
+    add("gen.ss", g["ss.embedding.weight"].view(512, 128, 7, 7), g["ss.embedding.bias"])
+    # SoftComp Linear: output column c*49+k -> k*128+c, so the fold kernel reads contiguous channels
+    perm = (torch.arange(49).view(49, 1) + 49 * torch.arange(128).view(1, 128)).reshape(-1)
+    add("gen.sc.embedding", g["sc.embedding.weight"][perm].view(6272, 512, 1, 1), g["sc.embedding.bias"][perm])
+    add("gen.sc.bias_conv", g["sc.bias_conv.weight"], g["sc.bias_conv.bias"])
+    for d in ("backward_1", "forward_1"):
+        add_align(f"gen.fp.{d}", g, fp + "deform_align." + d)
+        add(f"gen.fp.{d}.backbone.0", g[fp + f"backbone.{d}.0.weight"], g[fp + f"backbone.{d}.0.bias"], 1,
+            _pad_map(258, 264))
+        add(f"gen.fp.{d}.backbone.1", g[fp + f"backbone.{d}.2.weight"], g[fp + f"backbone.{d}.2.bias"])
+    add("gen.fp.fuse.0", g[fp + "fuse.0.weight"], g[fp + "fuse.0.bias"], 1, _pad_map(258, 264))
+    add("gen.fp.fuse.1", g[fp + "fuse.2.weight"], g[fp + "fuse.2.bias"])
+    perm40 = (torch.arange(49).view(49, 1) + 49 * torch.arange(40).view(1, 40)).reshape(-1)
+    for b in range(Wspec.N_TRANSFORMER_BLOCKS):
+        t = f"transformers.transformer.{b}."
+        a = t + "attention."
+        o = f"gen.tf.{b}."
+        qkv_w = torch.cat([g[a + "query.weight"], g[a + "key.weight"], g[a + "value.weight"]], 0)
+        qkv_b = torch.cat([g[a + "query.bias"], g[a + "key.bias"], g[a + "value.bias"]], 0)
+        add(o + "qkv", qkv_w.view(1536, 512, 1, 1), qkv_b)
+        add(o + "kv", qkv_w[512:].reshape(1024, 512, 1, 1), qkv_b[512:])
+        add(o + "proj", g[a + "proj.weight"].view(512, 512, 1, 1), g[a + "proj.bias"])
+        add(o + "fc1", g[t + "mlp.fc1.0.weight"][perm40].view(1960, 512, 1, 1), g[t + "mlp.fc1.0.bias"][perm40])
+        add(o + "fc2", g[t + "mlp.fc2.1.weight"].view(512, 40, 7, 7), g[t + "mlp.fc2.1.bias"])
+        for n in ("norm1", "norm2"):
+            tens[o + n + ".weight"] = g[t + n + ".weight"].float()
+            tens[o + n + ".bias"] = g[t + n + ".bias"].float()
+        tens[o + "pool.weight"] = g[a + "pool_layer.weight"].reshape(512, 16).float()
+        tens[o + "pool.bias"] = g[a + "pool_layer.bias"].float()
+        expect = torch.from_numpy(Wspec.rolled_valid_indices())
+        if not torch.equal(g[a + "valid_ind_rolled"].cpu().long(), expect):
+            raise ValueError("checkpoint's valid_ind_rolled differs from the 5x9 window ring this engine implements")
+    return convs, tens
+
+
+# ----------------------------------------------------------------------------------------------
+# engine
+# ----------------------------------------------------------------------------------------------
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One engine per process/GPU.  Owns the workspace arena and the packed weights."""
+
+    def __init__(self, device: torch.device | str | int = "cuda:0", workspace_gb: float = 48.0):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("the ProPainter B200 engine needs a CUDA device (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._keep = []
+        total = torch.cuda.get_device_properties(self.device).total_memory
+        nbytes = int(min(workspace_gb * (1 << 30), total * 0.6))
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        h = ctypes.c_void_p()
+        self._check(self.lib.pp_create(self.device.index, _ptr(self.workspace), nbytes, ctypes.byref(h)))
+        self.h = h
+        self.conv_meta: Dict[str, dict] = {}
+
+    # -- helpers
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError("propainter_b200: " + self.lib.pp_last_error().decode())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights
+    def register_conv(self, name, w, b, groups=1, cin_map=None):
+        packed, meta = pack_conv_weight(w, groups, cin_map)
+        packed = packed.to(self.device)
+        bias = None if b is None else b.detach().float().contiguous().to(self.device)
+        self._keep += [packed, bias]
+        self.conv_meta[name] = meta
+        self._check(self.lib.pp_register_conv(self.h, name.encode(), _ptr(packed), _ptr(bias), meta["cout_g"],
+                                              meta["cout_g_pad"], meta["bn"], meta["cin_g"], meta["kh"], meta["kw"],
+                                              meta["groups"]))
+
+    def register_tensor(self, name, t):
+        t = t.detach().float().contiguous().to(self.device)
+        self._keep.append(t)
+        self._check(self.lib.pp_register_tensor(self.h, name.encode(), _ptr(t), t.numel() * 4))
+
+    def load_weights(self, raft_sd, rfc_sd, gen_sd):
+        convs, tens = build_layers(raft_sd, rfc_sd, gen_sd)
+        for name, (w, b, groups, cin_map) in convs.items():
+            self.register_conv(name, w, b, groups, cin_map)
+        for name, t in tens.items():
+            self.register_tensor(name, t)
+        return self
+
+    # -- stages (float32 contiguous CUDA tensors in the reference's layouts)
+    def _f32(self, t):
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def raft_bidir(self, frames: torch.Tensor, iters: int):
+        """frames [T,3,H,W] in [-1,1] -> (flows_f, flows_b) [T-1,2,H,W]."""
+        frames = self._f32(frames)
+        T, _, H, W = frames.shape
+        ff = torch.empty(T - 1, 2, H, W, device=self.device, dtype=torch.float32)
+        fb = torch.empty_like(ff)
+        self._check(self.lib.pp_raft_bidir(self.h, _ptr(frames), T, H, W, int(iters), _ptr(ff), _ptr(fb), self._stream()))
+        return ff, fb
+
+    def flow_complete(self, flows_f, flows_b, flow_masks):
+        flows_f, flows_b, flow_masks = self._f32(flows_f), self._f32(flows_b), self._f32(flow_masks)
+        T, _, H, W = flow_masks.shape
+        assert flows_f.shape[0] == T - 1
+        of, ob = torch.empty_like(flows_f), torch.empty_like(flows_b)
+        self._check(self.lib.pp_flow_complete(self.h, _ptr(flows_f), _ptr(flows_b), _ptr(flow_masks), T, H, W, _ptr(of),
+                                              _ptr(ob), self._stream()))
+        return of, ob
+
+    def image_propagate(self, frames, masks, flows_f, flows_b):
+        frames, masks, flows_f, flows_b = map(self._f32, (frames, masks, flows_f, flows_b))
+        T, _, H, W = frames.shape
+        uf, um = torch.empty_like(frames), torch.empty_like(masks)
+        self._check(self.lib.pp_image_propagate(self.h, _ptr(frames), _ptr(masks), _ptr(flows_f), _ptr(flows_b), T, H, W,
+                                                _ptr(uf), _ptr(um), self._stream()))
+        return uf, um
+
+    def gen_begin(self, updated_frames, masks_dilated, updated_masks, flows_f, flows_b):
+        a = [self._f32(x) for x in (updated_frames, masks_dilated, updated_masks, flows_f, flows_b)]
+        T, _, H, W = a[0].shape
+        self._gen_shape = (T, H, W)
+        self._gen_inputs = a  # keep alive for the session
+        self._check(self.lib.pp_gen_begin(self.h, *[_ptr(x) for x in a], T, H, W, self._stream()))
+
+    def gen_window(self, frame_ids, l_t: int) -> torch.Tensor:
+        """-> fp16 [l_t,H,W,4] (rgb in [-1,1], lane 3 unused)."""
+        T, H, W = self._gen_shape
+        ids = (ctypes.c_int * len(frame_ids))(*[int(i) for i in frame_ids])
+        pred = torch.empty(l_t, H, W, 4, device=self.device, dtype=torch.float16)
+        self._check(self.lib.pp_gen_window(self.h, ids, len(frame_ids), int(l_t), _ptr(pred), self._stream()))
+        return pred
+
+    def gen_end(self):
+        self._check(self.lib.pp_gen_end(self.h))
+        self._gen_inputs = None
+
+    def composite(self, pred, masks_dilated, orig_u8, comp_u8, frame_ids_dev, first_visit_dev):
+        l_t, H, W, _ = pred.shape
+        self._check(self.lib.pp_composite(self.h, _ptr(pred), _ptr(masks_dilated), _ptr(orig_u8), _ptr(comp_u8),
+                                          _ptr(frame_ids_dev), _ptr(first_visit_dev), l_t, H, W, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pp_launch_count(self.h))
+
+    @property
+    def workspace_peak(self) -> int:
+        return int(self.lib.pp_workspace_peak(self.h))
+
+    # -- single operators (tests / micro-benchmarks)
+    def op_conv(self, name, x_nhwc, stride=1, pad=0, dil=1, replicate=False, act=ACT_NONE, slope=0.0, residual=None):
+        m = self.conv_meta[name]
+        N, H, W, _ = x_nhwc.shape
+        kh, kw = m["kh"], m["kw"]
+        OH = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        OW = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+        out = torch.empty(N, OH, OW, m["cout_g"] * m["groups"], device=self.device, dtype=torch.float16)
+        self._check(self.lib.pp_op_conv(self.h, name.encode(), _ptr(x_nhwc), N, H, W, stride, pad, dil, int(replicate),
+                                        act, float(slope), _ptr(residual), _ptr(out), self._stream()))
+        return out
+
+    def op_corr_lookup(self, levels, coords, h8, w8):
+        nq = coords.shape[0]
+        out = torch.empty(nq, 328, device=self.device, dtype=torch.float16)
+        self._check(self.lib.pp_op_corr_lookup(self.h, *[_ptr(l) for l in levels], _ptr(coords), _ptr(out), nq, h8, w8,
+                                               self._stream()))
+        return out
+
+    def op_imgprop_step(self, cur4, prop4, flow_prop, flow_check):
+        H, W, _ = cur4.shape
+        out = torch.empty_like(cur4)
+        self._check(self.lib.pp_op_imgprop_step(self.h, _ptr(cur4), _ptr(prop4), _ptr(out), _ptr(flow_prop),
+                                                _ptr(flow_check), H, W, self._stream()))
+        return out
+
+    def op_attention(self, qkv, pkv, win_flags, t, gh, gw, n_pool, parity):
+        out = torch.zeros(t, gh, gw, 512, device=self.device, dtype=torch.float16)
+        self._check(self.lib.pp_op_attention(self.h, _ptr(qkv), _ptr(pkv), _ptr(out), _ptr(win_flags), t, gh, gw, n_pool,
+                                             parity, self._stream()))
+        return out

@@ -1,0 +1,94 @@
+/* C ABI of the B200-native ProPainter inference path (libpropainter_b200.so).
+ *
+ * Every entry point takes raw device pointers, sizes and a CUDA stream (as void*, 0 = legacy default
+ * stream) and returns 0 on success; on failure pp_last_error() holds a message.  No torch types cross this
+ * boundary.  Tensors are contiguous, float32, in the layouts the reference's own tensors have at the same
+ * call sites (paths relative to daniabib/ComfyUI_ProPainter_Nodes):
+ *
+ *   pp_raft_bidir          replaces  raft_model(frames, iters)                propainter_inference.py:77-93
+ *                                    (RAFT_bi.forward, model/modules/flow_comp_raft.py:39-58)
+ *   pp_flow_complete       replaces  forward_bidirect_flow + combine_flow     propainter_inference.py:123-150
+ *                                    (model/recurrent_flow_completion.py:356-400)
+ *   pp_image_propagate     replaces  img_propagation + blend                  propainter_inference.py:186-219
+ *                                    (model/propainter.py:350-356, 118-231)
+ *   pp_gen_begin/window    replace   inpaint_model(selected_imgs, ...)        propainter_inference.py:272-281
+ *                                    (InpaintGenerator.forward, model/propainter.py:358-453)
+ *   pp_composite           replaces  the numpy composite                      propainter_inference.py:283-307
+ *   pp_register_*          replace   load_state_dict of the three checkpoints utils/model_utils.py:49-59
+ */
+#ifndef PROPAINTER_B200_H
+#define PROPAINTER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PP_API __attribute__((visibility("default")))
+#else
+#define PP_API
+#endif
+
+typedef struct PPEngine* pp_handle;
+
+/* Message of the last failing call on this thread. */
+PP_API const char* pp_last_error(void);
+/* Library build id ("propainter_b200 <n> sm_100a"). */
+PP_API const char* pp_version(void);
+
+/* Create an engine on `device` whose scratch arena is the caller-allocated device buffer
+ * [workspace, workspace + workspace_bytes) (256-byte aligned). */
+PP_API int pp_create(int device, void* workspace, size_t workspace_bytes, pp_handle* out);
+PP_API int pp_destroy(pp_handle h);
+
+/* Register packed weights (device memory owned by the caller, must outlive the handle).
+ * `w` is the 128B-swizzled tile image produced by comfyui_propainter_nodes_b200.weights_pack,
+ * [groups][ceil(kh*kw*cin_g/64)][cout_g_pad] rows of 64 fp16; `bias` is float32 [groups*cout_g] or NULL. */
+PP_API int pp_register_conv(pp_handle h, const char* name, const void* w, const float* bias, int cout_g, int cout_g_pad,
+                     int bn, int cin_g, int kh, int kw, int groups);
+PP_API int pp_register_tensor(pp_handle h, const char* name, const void* ptr, size_t bytes);
+
+/* frames [T,3,H,W] in [-1,1]  ->  flows_f, flows_b [T-1,2,H,W]. */
+PP_API int pp_raft_bidir(pp_handle h, const float* frames, int T, int H, int W, int iters, float* flows_f, float* flows_b,
+                  void* stream);
+/* flows [T-1,2,H,W], flow_masks [T,1,H,W]  ->  completed flows [T-1,2,H,W] (prediction inside the mask). */
+PP_API int pp_flow_complete(pp_handle h, const float* flows_f, const float* flows_b, const float* flow_masks, int T, int H,
+                     int W, float* out_f, float* out_b, void* stream);
+/* frames [T,3,H,W], masks [T,1,H,W], completed flows  ->  updated frames [T,3,H,W], updated masks [T,1,H,W]. */
+PP_API int pp_image_propagate(pp_handle h, const float* frames, const float* masks, const float* flows_f,
+                       const float* flows_b, int T, int H, int W, float* updated_frames, float* updated_masks,
+                       void* stream);
+/* Generator session over one clip: encodes all T frames once. */
+PP_API int pp_gen_begin(pp_handle h, const float* updated_frames, const float* masks_dilated, const float* updated_masks,
+                 const float* flows_f, const float* flows_b, int T, int H, int W, void* stream);
+/* One sliding window: frame_ids[0..l_t) are consecutive local frames, frame_ids[l_t..t) reference frames
+ * (host array).  pred is fp16 [l_t][H][W][4] (rgb in [-1,1] + 1 unused lane). */
+PP_API int pp_gen_window(pp_handle h, const int* frame_ids, int t, int l_t, void* pred_f16, void* stream);
+PP_API int pp_gen_end(pp_handle h);
+/* uint8 composite with the reference's truncation / 0.5-0.5 blending order.  frame_ids / first_visit are
+ * device int32 arrays of length l_t; orig / comp are uint8 [T][H][W][3]; masks float32 [T,1,H,W]. */
+PP_API int pp_composite(pp_handle h, const void* pred_f16, const float* masks_dilated, const uint8_t* orig, uint8_t* comp,
+                 const int* frame_ids_dev, const int* first_visit_dev, int l_t, int H, int W, void* stream);
+
+/* Kernels launched by this handle since creation (bench accounting), and the arena high-water mark. */
+PP_API long long pp_launch_count(pp_handle h);
+PP_API size_t pp_workspace_peak(pp_handle h);
+
+/* ---- single-operator entry points (unit tests and micro-benchmarks) ------------------------------------ */
+/* Generic conv / linear through the tcgen05 implicit-GEMM kernel: x NHWC fp16 [N,H,W,cin_g*groups]. */
+PP_API int pp_op_conv(pp_handle h, const char* name, const void* x_f16, int N, int H, int W, int stride, int pad, int dil,
+               int replicate, int act, float slope, const void* residual_f16, void* out_f16, void* stream);
+PP_API int pp_op_corr_lookup(pp_handle h, const void* l0, const void* l1, const void* l2, const void* l3,
+                      const float* coords, void* out_f16, long long nq, int h8, int w8, void* stream);
+PP_API int pp_op_imgprop_step(pp_handle h, const void* cur4_f16, const void* prop_in4_f16, void* prop_out4_f16,
+                       const void* flow_prop_f16, const void* flow_check_f16, int H, int W, void* stream);
+PP_API int pp_op_attention(pp_handle h, const void* qkv_f16, const void* pkv_f16, void* out_f16, const int* win_flags_dev,
+                    int t, int gh, int gw, int n_pool, int parity, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROPAINTER_B200_H */

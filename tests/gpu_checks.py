@@ -1,0 +1,277 @@
+"""GPU parity checks shared by the pytest -m gpu tests and the diagnostic report (python -m tests.gpu_checks).
+
+Every check returns a dict of error statistics of the CUDA path (through the C ABI) against the CPU oracle
+or a plain PyTorch fp32 evaluation of the same operator on the same fp16-rounded inputs."""
+import math
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from comfyui_propainter_nodes_b200 import engine as E
+from comfyui_propainter_nodes_b200 import weights as Wt
+from comfyui_propainter_nodes_b200 import propainter_inference as PI
+from comfyui_propainter_nodes_b200.utils import image_utils as IU
+from comfyui_propainter_nodes_b200.utils.model_utils import Models, StageHandle
+from oracle import propainter_oracle as O
+from tests.golden import cases
+
+DEV = "cuda:0"
+_ENG = {}
+
+
+def bare_engine():
+    if "bare" not in _ENG:
+        _ENG["bare"] = E.Engine(DEV, workspace_gb=2.0)
+    return _ENG["bare"]
+
+
+def full_models():
+    if "full" not in _ENG:
+        eng = E.Engine(DEV, workspace_gb=16.0).load_weights(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
+                                                           Wt.synthetic_generator_state_dict())
+        _ENG["full"] = Models(StageHandle(eng, "raft"), StageHandle(eng, "flow"), StageHandle(eng, "inpaint"))
+    return _ENG["full"]
+
+
+def stats(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    d = (a - b).abs()
+    return dict(max_abs=float(d.max()), mean_abs=float(d.mean()), ref_mean_abs=float(b.abs().mean()),
+                rel=float(d.max() / (b.abs().max() + 1e-12)), nan=bool(torch.isnan(a).any()))
+
+
+# ------------------------------------------------------------------------------------------------ conv
+CONV_CASES = {
+    # name: (N, H, W, Cin_ref, Cout, kh, kw, stride, pad, dil, groups, replicate, act, slope, residual, cin_pad_to)
+    "linear_512_1536": (1, 1, 1000, 512, 1536, 1, 1, 1, 0, 1, 1, 0, E.ACT_NONE, 0.0, False, None),
+    "conv3x3_128_128_lrelu_res": (2, 45, 80, 128, 128, 3, 3, 1, 1, 1, 1, 0, E.ACT_LRELU, 0.2, True, None),
+    "conv7x7_s2_3_64": (2, 64, 96, 3, 64, 7, 7, 2, 3, 1, 1, 0, E.ACT_RELU, 0.0, False, 8),
+    "conv3x3_dil3": (1, 45, 80, 128, 128, 3, 3, 1, 3, 3, 1, 0, E.ACT_LRELU, 0.2, False, None),
+    "conv5x5_s2_replicate": (2, 64, 96, 3, 32, 5, 5, 2, 2, 1, 1, 1, E.ACT_LRELU, 0.2, False, 8),
+    "grouped_g4": (1, 30, 40, 768, 384, 3, 3, 1, 1, 1, 4, 0, E.ACT_LRELU, 0.2, False, None),
+    "cout2": (1, 64, 96, 32, 2, 3, 3, 1, 1, 1, 1, 0, E.ACT_NONE, 0.0, False, None),
+    "cout126": (1, 45, 80, 256, 126, 3, 3, 1, 1, 1, 1, 0, E.ACT_RELU, 0.0, False, None),
+    "cout432": (1, 45, 80, 128, 432, 3, 3, 1, 1, 1, 1, 0, E.ACT_NONE, 0.0, False, None),
+    "cin261": (1, 44, 80, 261, 128, 3, 3, 1, 1, 1, 1, 0, E.ACT_LRELU, 0.1, False, 264),
+    "conv7x7_s3_40_512": (2, 44, 80, 40, 512, 7, 7, 3, 3, 1, 1, 0, E.ACT_NONE, 0.0, True, None),
+    "conv1x5": (1, 45, 80, 384, 256, 1, 5, 1, (0, 2), 1, 1, 0, E.ACT_SIGMOID, 0.0, False, None),
+    "conv5x1_tanh": (1, 45, 80, 384, 128, 5, 1, 1, (2, 0), 1, 1, 0, E.ACT_TANH, 0.0, False, None),
+    "k2304": (1, 45, 80, 2304, 128, 1, 1, 1, 0, 1, 1, 0, E.ACT_NONE, 0.0, False, None),
+}
+
+
+def check_conv(name):
+    (N, H, W, cin, cout, kh, kw, s, pad, dil, groups, rep, act, slope, use_res, cin_pad) = CONV_CASES[name]
+    eng = bare_engine()
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    w = torch.randn(cout, cin // groups, kh, kw, generator=g) / math.sqrt(cin // groups * kh * kw)
+    b = torch.randn(cout, generator=g) * 0.1
+    x = torch.randn(N, cin, H, W, generator=g)
+    cin_k = cin if cin_pad is None else cin_pad
+    cmap = None if cin_pad is None else list(range(cin)) + [-1] * (cin_pad - cin)
+    eng.register_conv("t." + name, w, b, groups, cmap)
+    xh = torch.zeros(N, H, W, cin_k, dtype=torch.float16)
+    xh[..., :cin] = x.permute(0, 2, 3, 1).half()
+    xh = xh.to(DEV)
+    ph, pw = (pad if isinstance(pad, tuple) else (pad, pad))
+    # torch reference on the fp16-rounded operands, fp32 math
+    xr, wr = x.half().float().to(DEV), w.half().float().to(DEV)
+    if rep:
+        xr = F.pad(xr, (pw, pw, ph, ph), mode="replicate")
+        ref = F.conv2d(xr, wr, b.to(DEV), s, 0, dil, groups)
+    else:
+        ref = F.conv2d(xr, wr, b.to(DEV), s, (ph, pw), dil, groups)
+    res = None
+    if act == E.ACT_RELU: ref = F.relu(ref)
+    elif act == E.ACT_LRELU: ref = F.leaky_relu(ref, slope)
+    elif act == E.ACT_SIGMOID: ref = torch.sigmoid(ref)
+    elif act == E.ACT_TANH: ref = torch.tanh(ref)
+    if use_res:
+        res = torch.randn(ref.shape, generator=g).permute(0, 2, 3, 1).contiguous().half().to(DEV)
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    if ph != pw:
+        # op_conv takes a single pad; asymmetric kernels go through the lower-level builder in the stages.
+        # Emulate with explicit zero padding of the input.
+        xh = F.pad(xh, (0, 0, pw, pw, ph, ph))
+        out = eng.op_conv("t." + name, xh.contiguous(), s, 0, dil, bool(rep), act, slope, res)
+    else:
+        out = eng.op_conv("t." + name, xh, s, ph, dil, bool(rep), act, slope, res)
+    torch.cuda.synchronize()
+    return stats(out.permute(0, 3, 1, 2), ref)
+
+
+# ------------------------------------------------------------------------------------------------ HBM kernels
+def check_corr_lookup():
+    eng = bare_engine()
+    g = torch.Generator().manual_seed(3)
+    B, h8, w8 = 2, 22, 40
+    P = h8 * w8
+    f1, f2 = torch.randn(B, 64, h8, w8, generator=g), torch.randn(B, 64, h8, w8, generator=g)
+    pyr = [p.half().float() for p in O.corr_pyramid(f1, f2)]  # level-wise fp16 rounding like the CUDA path stores
+    coords = torch.stack(torch.meshgrid(torch.arange(w8), torch.arange(h8), indexing="xy"), 0).float()[None].repeat(B, 1, 1, 1)
+    coords = coords + 6 * torch.randn(B, 2, h8, w8, generator=g)
+    ref = O.corr_lookup(pyr, coords)  # [B,324,h,w]
+    lv = [p.reshape(B * P, -1).half().to(DEV).contiguous() for p in pyr]
+    cd = coords.permute(0, 2, 3, 1).reshape(B * P, 2).contiguous().to(DEV)
+    out = eng.op_corr_lookup(lv, cd, h8, w8)
+    torch.cuda.synchronize()
+    st = stats(out[:, :324].reshape(B, h8, w8, 324).permute(0, 3, 1, 2), ref)
+    st["pad_zero"] = float(out[:, 324:].abs().max())
+    return st
+
+
+def check_imgprop_step():
+    eng = bare_engine()
+    H, W = 48, 64
+    frames, m, (ff, fb) = cases.imgprop_case()
+    cur = (frames[0, 1] * (1 - m[0, 1])).half().float()
+    prop = (frames[0, 2] * (1 - m[0, 2])).half().float()
+    mc, mp = m[0, 1], m[0, 2]
+    fp_, fc_ = ff[0, 1].half().float(), fb[0, 1].half().float()
+    valid = O.fb_consistency(fp_[None], fc_[None])
+    warped = O.warp_by_flow(prop[None], fp_[None].permute(0, 2, 3, 1), "nearest")
+    mv = O._bin(O.warp_by_flow(mp[None], fp_[None].permute(0, 2, 3, 1)))
+    u = O._bin(mc[None] * valid * (1 - mv))
+    ref_f = u * warped + (1 - u) * cur[None]
+    ref_m = O._bin(mc[None] * (1 - valid * (1 - mv)))
+    pack = lambda f, k: torch.cat([f, k], 0).permute(1, 2, 0).contiguous().half().to(DEV)
+    n2 = lambda f: f.permute(1, 2, 0).contiguous().half().to(DEV)
+    out = eng.op_imgprop_step(pack(cur, mc), pack(prop, mp), n2(fp_), n2(fc_)).float().cpu()
+    d = (out[..., :3].permute(2, 0, 1) - ref_f[0]).abs()
+    return dict(frame_mismatch_frac=float((d.max(0).values > 1e-3).float().mean()), max_abs=float(d.max()),
+                mask_mismatch_frac=float((out[..., 3] != ref_m[0, 0]).float().mean()))
+
+
+def check_attention():
+    eng = bare_engine()
+    g = torch.Generator().manual_seed(5)
+    t, gh, gw, C = 5, 8, 12, 512     # padded grid 10 x 18 -> 4 windows, pooled 2 x 4
+    nh, nw = 10, 18
+    x = torch.randn(1, t, gh, gw, C, generator=g).half().float()
+    sd = {}
+    p = "a."
+    eye = torch.eye(C)
+    for n in ("query", "key", "value", "proj"):
+        sd[p + n + ".weight"], sd[p + n + ".bias"] = eye, torch.zeros(C)
+    sd[p + "pool_layer.weight"] = torch.full((C, 1, 4, 4), 1 / 16.0) + 0.02 * torch.randn(C, 1, 4, 4, generator=g)
+    sd[p + "pool_layer.bias"] = 0.1 * torch.randn(C, generator=g)
+    sd[p + "valid_ind_rolled"] = torch.from_numpy(Wt.rolled_valid_indices())
+    mask = torch.zeros(1, 3, gh, gw, 1)
+    mask[0, :, 1:3, 2:5] = 1  # only window (0,0) is masked
+    res = {}
+    for parity in (0, 1):
+        t_ind = torch.arange(parity, t, 2)
+        ref = O.sparse_window_attention(sd, p, x, mask, t_ind)
+        xp = F.pad(x, (0, 0, 0, nw - gw, 0, nh - gh))
+        px = F.conv2d(xp.view(t, nh, nw, C).permute(0, 3, 1, 2), sd[p + "pool_layer.weight"], sd[p + "pool_layer.bias"],
+                      stride=4, groups=C)
+        n_pool = px.shape[-2] * px.shape[-1]
+        pkv = px.permute(0, 2, 3, 1).reshape(t, n_pool, C)
+        qkv = torch.cat([xp, xp, xp], -1).view(t, nh * nw, 3 * C).half().to(DEV).contiguous()
+        pkv2 = torch.cat([pkv, pkv], -1).half().to(DEV).contiguous()
+        flags = torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=DEV)
+        out = eng.op_attention(qkv, pkv2, flags, t, gh, gw, n_pool, parity)
+        torch.cuda.synchronize()
+        res[f"parity{parity}"] = stats(out[None], ref)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------ stages
+def check_raft(golden):
+    m = full_models()
+    fr = cases.raft_case()
+    ff, fb = m.raft_model.engine.raft_bidir(fr[0].to(DEV), cases.RAFT_ITERS)
+    torch.cuda.synchronize()
+    return dict(fwd=stats(ff[None], torch.from_numpy(golden["raft_ff"])), bwd=stats(fb[None], torch.from_numpy(golden["raft_fb"])))
+
+
+def check_rfc(golden):
+    m = full_models()
+    (ff, fb), masks = cases.rfc_case()
+    of, ob = m.flow_model.engine.flow_complete(ff[0].to(DEV), fb[0].to(DEV), masks[0].to(DEV))
+    torch.cuda.synchronize()
+    return dict(fwd=stats(of[None], torch.from_numpy(golden["rfc_f"])), bwd=stats(ob[None], torch.from_numpy(golden["rfc_b"])))
+
+
+def check_imgprop(golden):
+    m = full_models()
+    frames, mk, (ff, fb) = cases.imgprop_case()
+    uf, um = m.inpaint_model.engine.image_propagate(frames[0].to(DEV), mk[0].to(DEV), ff[0].to(DEV), fb[0].to(DEV))
+    torch.cuda.synchronize()
+    d = (uf.cpu() - torch.from_numpy(golden["imgprop_frames"])[0]).abs().max(1).values
+    return dict(frame_mismatch_frac=float((d > 2e-3).float().mean()), frame_max_abs=float(d.max()),
+                mask_mismatch_frac=float((um.cpu() != torch.from_numpy(golden["imgprop_masks"])[0]).float().mean()))
+
+
+def check_window(golden):
+    m = full_models()
+    eng = m.inpaint_model.engine
+    c = cases.window_case()
+    t, l_t = c["frames"].shape[1], c["l_t"]
+    # the session API wants flows for all T-1 pairs; only the local ones are used
+    H, W = c["frames"].shape[-2:]
+    ff = torch.zeros(t - 1, 2, H, W)
+    fb = torch.zeros(t - 1, 2, H, W)
+    ff[:l_t - 1], fb[:l_t - 1] = c["flows"][0][0], c["flows"][1][0]
+    eng.gen_begin(c["frames"][0].to(DEV), c["masks_in"][0].to(DEV), c["masks_upd"][0].to(DEV), ff.to(DEV), fb.to(DEV))
+    pred = eng.gen_window(list(range(t)), l_t)
+    eng.gen_end()
+    torch.cuda.synchronize()
+    out = pred[..., :3].permute(0, 3, 1, 2).float()
+    return stats(out[None], torch.from_numpy(golden["window_pred"]))
+
+
+def check_e2e(golden):
+    m = full_models()
+    e = cases.e2e_case()
+    icfg = IU.ImageConfig(e["W"], e["H"], 5, 8, (e["W"], e["H"]), e["T"])
+    ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(e["image"]), e["mask"], icfg, torch.device(DEV))
+    cfg = PI.ProPainterConfig(e["ref_stride"], e["neighbor_length"], e["subvideo_length"], e["raft_iter"], "enable",
+                              e["T"], torch.device(DEV), icfg.process_size)
+    uf, um, flows = PI.process_inpainting(m, ft, fm, md, cfg)
+    comp = PI.feature_propagation(m.inpaint_model, uf, um, md, flows, orig, cfg)
+    torch.cuda.synchronize()
+    a, b = np.stack(comp).astype(np.float64), golden["e2e_frames_u8"].astype(np.float64)
+    mse = ((a - b) ** 2).mean()
+    hole = golden["e2e_masks_dilated"][0, :, 0] > 0.5
+    mse_hole = (((a - b) ** 2).sum(-1)[hole]).mean() / 3
+    return dict(psnr=float(10 * np.log10(255 ** 2 / max(mse, 1e-12))),
+                psnr_hole=float(10 * np.log10(255 ** 2 / max(mse_hole, 1e-12))),
+                max_abs_u8=float(np.abs(a - b).max()), frac_gt1=float((np.abs(a - b) > 1).mean()),
+                flow=stats(flows[0].float(), torch.from_numpy(golden["e2e_pred_flow_f"])),
+                upd_frames=stats(uf.float(), torch.from_numpy(golden["e2e_updated_frames"])))
+
+
+def main():
+    import json
+    import os
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+    only = sys.argv[1:]
+    checks = [(f"conv:{n}", (lambda n=n: check_conv(n))) for n in CONV_CASES]
+    checks += [("corr_lookup", check_corr_lookup), ("imgprop_step", check_imgprop_step), ("attention", check_attention),
+               ("raft", lambda: check_raft(golden)), ("rfc", lambda: check_rfc(golden)),
+               ("imgprop", lambda: check_imgprop(golden)), ("window", lambda: check_window(golden)),
+               ("e2e", lambda: check_e2e(golden))]
+    for name, fn in checks:
+        if only and not any(o in name for o in only):
+            continue
+        t0 = time.time()
+        try:
+            r = fn()
+            print(f"[{name}] {time.time() - t0:.2f}s {json.dumps(r)}", flush=True)
+        except Exception as ex:  # keep going: one report per GPU call
+            print(f"[{name}] FAILED {type(ex).__name__}: {ex}", flush=True)
+            traceback.print_exc()
+            try:
+                torch.cuda.synchronize()
+            except Exception as ex2:
+                print("CUDA context is broken, stopping:", ex2, flush=True)
+                break
+
+
+if __name__ == "__main__":
+    main()

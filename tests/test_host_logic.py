@@ -1,0 +1,144 @@
+"""CPU tests: C-ABI library exports, weight packing, node surface, window scheduling, image utils."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from comfyui_propainter_nodes_b200 import engine as E
+from comfyui_propainter_nodes_b200 import weights as Wt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "propainter_b200.h")).read()
+    declared = sorted(set(re.findall(r"PP_API [a-z_ \*]+?(pp_[a-z_0-9]+)\(", hdr)))
+    assert declared, "no declarations found"
+    assert declared == E.exported_symbols(), (declared, E.exported_symbols())
+    lib = ctypes.CDLL(E.LIB_PATH)          # loads without a GPU
+    for name in declared:
+        getattr(lib, name)                 # raises if not exported
+    E.load_library()
+    assert b"sm_100a" in E.load_library().pp_version()
+
+
+def _unpack(packed, meta):
+    G, kc, rows = packed.shape[0], packed.shape[1], packed.shape[2]
+    pos = torch.arange(8).view(1, 8) ^ (torch.arange(rows).view(-1, 1) & 7)
+    un = torch.gather(packed.float(), 3, pos.view(1, 1, rows, 8, 1).expand(G, kc, rows, 8, 8))  # xor is an involution
+    return un.permute(0, 2, 1, 3, 4).reshape(G, rows, kc * 64)
+
+
+@pytest.mark.parametrize("cout,cin,k,groups,cin_pad", [(64, 3, 7, 1, 8), (384, 768, 3, 4, None), (126, 256, 3, 1, None),
+                                                       (432, 128, 3, 1, None), (1960, 512, 1, 1, None)])
+def test_pack_conv_weight_roundtrip(cout, cin, k, groups, cin_pad):
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(cout, cin // groups, k, k, generator=g)
+    cmap = None if cin_pad is None else list(range(cin)) + [-1] * (cin_pad - cin)
+    packed, meta = E.pack_conv_weight(w, groups, cmap)
+    assert meta["bn"] % 16 == 0 and meta["bn"] <= 256 and meta["cout_g_pad"] % meta["bn"] == 0
+    un = _unpack(packed, meta)
+    cin_k = meta["cin_g"]
+    K = k * k * cin_k
+    ref = torch.zeros(cout, k, k, cin_k)
+    ref[..., :cin // groups] = w.permute(0, 2, 3, 1)
+    ref = ref.reshape(groups, cout // groups, K).half().float()
+    assert torch.equal(un[:, :cout // groups, :K], ref)
+    assert float(un[:, cout // groups:].abs().max() if un.shape[1] > cout // groups else 0) == 0
+    assert float(un[:, :, K:].abs().max() if un.shape[2] > K else 0) == 0
+
+
+def test_build_layers_covers_checkpoints():
+    convs, tens = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
+                                 Wt.synthetic_generator_state_dict())
+    assert len(convs) == 150 and len(tens) == 8 * 6
+    # every kernel-side input channel count is a multiple of 8
+    for name, (w, b, groups, cmap) in convs.items():
+        cin = len(cmap) if cmap is not None else w.shape[1]
+        assert (cin + (-cin) % 8) % 8 == 0
+    # GRU gate merge: z|r stacked along Cout
+    assert convs["raft.update.gru.zr1"][0].shape == (256, 384, 1, 5)
+
+
+def test_bn_folding_matches_batchnorm():
+    sd = {k[7:]: v for k, v in Wt.synthetic_raft_state_dict().items()}
+    convs, _ = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
+                              Wt.synthetic_generator_state_dict())
+    w, b, _, _ = convs["raft.cnet.layer1.0.conv1"]
+    x = torch.randn(1, 64, 9, 11)
+    y = torch.nn.functional.conv2d(x, sd["cnet.layer1.0.conv1.weight"], sd["cnet.layer1.0.conv1.bias"], padding=1)
+    y = torch.nn.functional.batch_norm(y, sd["cnet.layer1.0.norm1.running_mean"], sd["cnet.layer1.0.norm1.running_var"],
+                                       sd["cnet.layer1.0.norm1.weight"], sd["cnet.layer1.0.norm1.bias"], False, 0.0, 1e-5)
+    y2 = torch.nn.functional.conv2d(x, w, b, padding=1)
+    assert (y - y2).abs().max() < 1e-4
+
+
+def test_strict_checkpoint_validation():
+    sd = Wt.synthetic_rfc_state_dict()
+    sd.pop("fusion.weight", None)
+    bad = dict(sd)
+    bad.pop("downsample.0.weight")
+    with pytest.raises(KeyError):
+        Wt.check_state_dict(bad, Wt.rfc_spec())
+
+
+def test_ring_indices_match_reference_buffer():
+    idx = Wt.rolled_valid_indices()
+    assert idx.shape == (148,) and idx[0] == 4  # first kept entry of the top-left mask is (row 0, col 4)
+
+
+def test_node_surface():
+    from comfyui_propainter_nodes_b200 import NODE_CLASS_MAPPINGS, NODE_DISPLAY_NAME_MAPPINGS
+    assert set(NODE_CLASS_MAPPINGS) == {"ProPainterInpaint", "ProPainterOutpaint"}
+    assert NODE_DISPLAY_NAME_MAPPINGS["ProPainterInpaint"] == "ProPainter Inpainting"
+    inp = NODE_CLASS_MAPPINGS["ProPainterInpaint"]
+    req = inp.INPUT_TYPES()["required"]
+    assert list(req) == ["image", "mask", "width", "height", "mask_dilates", "flow_mask_dilates", "ref_stride",
+                         "neighbor_length", "subvideo_length", "raft_iter", "fp16"]
+    assert req["width"][1] == {"default": 640, "min": 0, "max": 2560} and req["raft_iter"][1]["default"] == 20
+    assert inp.RETURN_TYPES == ("IMAGE", "MASK", "MASK") and inp.FUNCTION == "propainter_inpainting"
+    out = NODE_CLASS_MAPPINGS["ProPainterOutpaint"]
+    assert "mask" not in out.INPUT_TYPES()["required"] and out.RETURN_TYPES == ("IMAGE", "MASK", "INT", "INT")
+    assert out.INPUT_TYPES()["required"]["width_scale"][1]["default"] == 1.2
+
+
+def test_check_inputs_errors():
+    from comfyui_propainter_nodes_b200.propainter_nodes import check_inputs
+    with pytest.raises(Exception, match="greater than 1"):
+        check_inputs(torch.zeros(1, 8, 8, 3), torch.zeros(1, 8, 8))
+    with pytest.raises(Exception, match="same length"):
+        check_inputs(torch.zeros(4, 8, 8, 3), torch.zeros(3, 8, 8))
+    with pytest.raises(Exception, match="same dimensions"):
+        check_inputs(torch.zeros(4, 8, 8, 3), torch.zeros(4, 8, 9))
+    check_inputs(torch.zeros(4, 8, 8, 3), torch.zeros(1, 8, 8))
+
+
+def test_window_schedule_matches_oracle():
+    from comfyui_propainter_nodes_b200 import propainter_inference as PI
+    from oracle import propainter_oracle as O
+    for T, nl, rs, sv in ((80, 10, 10, 80), (240, 10, 10, 80), (16, 10, 10, 80), (8, 4, 3, 80), (33, 6, 7, 20)):
+        cfg = PI.ProPainterConfig(rs, nl, sv, 20, "enable", T, torch.device("cpu"), (64, 64))
+        assert PI.window_schedule(cfg) == O.window_schedule(T, nl, rs, sv)
+
+
+def test_engine_refuses_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.Engine("cuda:0")
+
+
+def test_outpaint_canvas():
+    from comfyui_propainter_nodes_b200.utils import image_utils as IU
+    from comfyui_propainter_nodes_b200.synthetic import synthetic_clip
+    img = synthetic_clip(3, 64, 96, 1)
+    cfg = IU.ImageOutpaintConfig(96, 64, 5, 8, (96, 64), 3, 1.5, 1.0)
+    assert cfg.outpaint_size == (144, 64)
+    canvas, fm, md = IU.extrapolation(IU.convert_image_to_frames(img), cfg)
+    a, f, m = np.array(canvas[0]), np.array(fm[0]), np.array(md[0])
+    assert a.shape == (64, 144, 3) and (a[:, :24] == 0).all() and (a[:, 24:120] > 0).any()
+    assert (m[:, :24] == 255).all() and (m[:, 24:120] == 0).all()
+    assert (f[:, :28] == 255).all() and (f[:, 28:116] == 0).all()   # 4-px inset of the flow mask
