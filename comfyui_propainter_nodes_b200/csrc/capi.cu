@@ -120,6 +120,41 @@ int pp_composite(pp_handle h, const void* pred_f16, const float* masks_dilated, 
 long long pp_launch_count(pp_handle h) { return h ? reinterpret_cast<PPEngine*>(h)->launches : 0; }
 size_t pp_workspace_peak(pp_handle h) { return h ? reinterpret_cast<PPEngine*>(h)->arena.peak : 0; }
 
+int pp_profile_enable(pp_handle h, int on) {
+  PP_HANDLE(h);
+  PP_CUDA_CHECK(cudaDeviceSynchronize());
+  for (auto& r : e.prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e.prof.clear();
+  e.profile = on != 0;
+  return PP_OK;
+}
+
+// Writes "name\tcount\tms\trows\tflops\tbytes\n" per kernel name (aggregated) into buf.
+int pp_profile_dump(pp_handle h, char* buf, size_t cap) {
+  PP_HANDLE(h);
+  PP_REQUIRE(buf != nullptr && cap > 0, "pp_profile_dump: no buffer");
+  PP_CUDA_CHECK(cudaDeviceSynchronize());
+  struct Agg { long long n = 0; double ms = 0, rows = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : e.prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+    Agg& a = agg[r.name];
+    a.n++; a.ms += ms; a.rows += r.rows; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& kv : agg) {
+    char line[512];
+    int n = snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%.0f\t%.0f\t%.0f\n", kv.first.c_str(), kv.second.n,
+                     kv.second.ms, kv.second.rows, kv.second.flops, kv.second.bytes);
+    if (off + n + 1 > cap) { pp_set_error("pp_profile_dump: buffer too small"); return PP_ERR_ARG; }
+    memcpy(buf + off, line, n + 1);
+    off += n;
+  }
+  return PP_OK;
+}
+
 // ---- single-operator entry points --------------------------------------------------------------------
 int pp_op_conv(pp_handle h, const char* name, const void* x_f16, int N, int H, int W, int stride, int pad, int dil,
                int replicate, int act, float slope, const void* residual_f16, void* out_f16, void* stream) {

@@ -1,4 +1,6 @@
 // Engine plumbing: registries and the conv-call builder.
+#include <string.h>
+
 #include "engine.cuh"
 
 int pp_get_conv(PPEngine& e, const std::string& name, const PPPackedConv** out) {
@@ -21,7 +23,7 @@ int pp_get_tensor(PPEngine& e, const std::string& name, const void** out) {
   return PP_OK;
 }
 
-PPConvCall::PPConvCall(PPEngine& e, const std::string& name, int N, int H, int W) : eng(&e) {
+PPConvCall::PPConvCall(PPEngine& e, const std::string& name_, int N, int H, int W) : eng(&e), name(name_) {
   memset(&p, 0, sizeof(p));
   const PPPackedConv* w = nullptr;
   err = pp_get_conv(e, name, &w);
@@ -90,5 +92,7 @@ int PPConvCall::run(cudaStream_t st) {
   p.OH = (p.H + 2 * p.ph - p.dh * (p.kh - 1) - 1) / p.sh + 1;
   p.OW = (p.W + 2 * p.pw - p.dw * (p.kw - 1) - 1) / p.sw + 1;
   eng->launches++;
+  const double rows = (double)p.N * p.OH * p.OW;
+  PPProfScope ps(*eng, "conv:" + name, rows, 2.0 * rows * p.Cout_g * p.groups * p.kh * p.kw * p.Cin, 0.0, st);
   return pp_launch_conv(p, st);
 }

@@ -54,6 +54,34 @@ struct PPEngine {
     int gh = 0, gw = 0, nh = 0, nw = 0, ph = 0, pw = 0;
   } gen;
   long long launches = 0;  // kernels launched by this engine (for bench accounting)
+  // optional per-kernel timing (CUDA events on the launch stream), see pp_profile_* in capi.cu
+  struct ProfRec {
+    std::string name;
+    cudaEvent_t a, b;
+    double rows, flops, bytes;
+  };
+  bool profile = false;
+  std::vector<ProfRec> prof;
+};
+
+// Times one kernel launch when profiling is enabled (events recorded on the launch stream).
+struct PPProfScope {
+  PPEngine& e;
+  cudaStream_t st;
+  bool on;
+  PPProfScope(PPEngine& eng, const std::string& name, double rows, double flops, double bytes, cudaStream_t s)
+      : e(eng), st(s), on(eng.profile) {
+    if (!on) return;
+    PPEngine::ProfRec r;
+    r.name = name; r.rows = rows; r.flops = flops; r.bytes = bytes;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    e.prof.push_back(r);
+  }
+  ~PPProfScope() {
+    if (on) cudaEventRecord(e.prof.back().b, st);
+  }
 };
 
 template <typename T>
@@ -74,6 +102,7 @@ int pp_get_tensor(PPEngine& e, const std::string& name, const void** out);
 struct PPConvCall {
   PPConvParams p;
   PPEngine* eng;
+  std::string name;
   int err = PP_OK;
   PPConvCall(PPEngine& e, const std::string& name, int N, int H, int W);
   PPConvCall& in(const __half* ptr, int cs, int co, int channels, int gstep = 0);

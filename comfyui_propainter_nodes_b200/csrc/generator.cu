@@ -187,14 +187,20 @@ int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __hal
         const __half* fprop = (mod == 0 ? g.flows_f4 : g.flows_b4) + (size_t)(f0 + fi) * P4 * 2;
         const __half* fchk = (mod == 0 ? g.flows_b4 : g.flows_f4) + (size_t)(f0 + fi) * P4 * 2;
         const __half* pprev = dst + (size_t)prev * fsz;
-        PP_TRY(pp_k_featprop_cond(cur, 128, pprev, 128, fprop, fchk, m2, 8, cond, 264, h4, w4, 128, st));
+        {
+          PPProfScope ps(e, "featprop_warp", (double)P4, 0.0, (double)P4 * (128 * 2 * 2 + 264 * 2 + 8 + 16), st);
+          PP_TRY(pp_k_featprop_cond(cur, 128, pprev, 128, fprop, fchk, m2, 8, cond, 264, h4, w4, 128, st));
+        }
         e.launches++;
         PP_TRY(PPConvCall(e, m + ".offset.0", 1, h4, w4).in(cond, 264, 0, 264).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
         PP_TRY(PPConvCall(e, m + ".offset.1", 1, h4, w4).in(o1, 128, 0, 128).out(o2, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
         PP_TRY(PPConvCall(e, m + ".offset.2", 1, h4, w4).in(o2, 128, 0, 128).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
         PP_TRY(PPConvCall(e, m + ".offset.3", 1, h4, w4).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
         // offsets = 3*tanh(.) + flow (dy,dx) (propainter.py:66-68); flow sits at cond[:, 256:258]
-        PP_TRY(pp_k_dcn_sample(pprev, 128, 0, 128, nullptr, 0, 0, 0, offs, 432, cond, 264, 256, 3.0f, cols, 1, h4, w4, st));
+        {
+          PPProfScope ps(e, "dcn_sample", (double)P4, 0.0, (double)P4 * (128 * 2 + 432 * 2 + 1152 * 2), st);
+          PP_TRY(pp_k_dcn_sample(pprev, 128, 0, 128, nullptr, 0, 0, 0, offs, 432, cond, 264, 256, 3.0f, cols, 1, h4, w4, st));
+        }
         e.launches++;
         PP_TRY(PPConvCall(e, m + ".dcn", 1, h4, w4).in(cols, 1152, 0, 1152).geom(1, 1, 0, 0).out(aligned, 128, 0).run(st));
         prop = aligned;
@@ -246,13 +252,21 @@ int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __hal
     PP_TRY(PPConvCall(e, b + "qkv", 1, 1, (int)rows_pad).in(xn, 512, 0, 512).out(qkv, 1536, 0).run(st));
     PP_TRY(pp_k_pool_tokens(xn, (const float*)pwt, (const float*)pbs, pooled, t, nh, nw, g.ph, g.pw, 512, st));
     PP_TRY(PPConvCall(e, b + "kv", 1, 1, t * np).in(pooled, 512, 0, 512).out(pkv, 1024, 0).run(st));
-    PP_TRY(pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, att, 512, g.win_flags, g.ring_idx, t,
-                          gh, gw, nh, nw, np, blk % 2, st));
+    {
+      // flops if every window were masked (upper bound; the masked fraction is data dependent)
+      const double nti = (t - blk % 2 + 1) / 2, nkeys = nti * (193 + np);
+      PPProfScope ps(e, "attention", (double)rows_pad, 4.0 * rows_pad * nkeys * 512, 0.0, st);
+      PP_TRY(pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, att, 512, g.win_flags, g.ring_idx,
+                            t, gh, gw, nh, nw, np, blk % 2, st));
+    }
     PP_TRY(PPConvCall(e, b + "proj", 1, 1, (int)rows).in(att, 512, 0, 512).out(x, 512, 0).residual(x, 512, 0).run(st));
     PP_TRY(pp_k_layernorm(x, (const float*)g2, (const float*)b2, y, rows, gh, gw, gh, gw, st));
     // FusionFeedForward (sparse_transformer.py:67-123): fc1 -> fold/normalise/(unfold) -> GELU -> fc2
     PP_TRY(PPConvCall(e, b + "fc1", 1, 1, (int)rows).in(y, 512, 0, 512).out(f1, 1960, 0).run(st));
-    PP_TRY(pp_k_fold(f1, 1960, img40, t, h4, w4, 40, gh, gw, 1, 1, st));
+    {
+      PPProfScope ps(e, "fold_ffn", (double)rows, 0.0, (double)rows * 1960 * 2 + (double)t * P4 * 40 * 2, st);
+      PP_TRY(pp_k_fold(f1, 1960, img40, t, h4, w4, 40, gh, gw, 1, 1, st));
+    }
     PP_TRY(PPConvCall(e, b + "fc2", t, h4, w4).in(img40, 40, 0, 40).geom(3, 3, 3, 3).out(x, 512, 0)
                .residual(x, 512, 0).run(st));
     e.launches += 5;

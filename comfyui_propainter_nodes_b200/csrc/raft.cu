@@ -175,7 +175,10 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
         // P*P may exceed int range only beyond 46340 pixels at 1/8 res (3.7 MPixel frames)
         PP_REQUIRE((long long)P * P < (1LL << 31), "raft: frame too large for the correlation volume indexing");
         p.out_gstep = P * P;
-        PP_TRY(pp_launch_conv(p, st));
+        {
+          PPProfScope ps(e, "conv:raft.corr", (double)M, 2.0 * M * P * 256, (double)M * P * 2 + 2.0 * M * 256 * 2, st);
+          PP_TRY(pp_launch_conv(p, st));
+        }
         e.launches++;
       }
       for (int l = 0; l < 3; ++l) {
@@ -201,7 +204,11 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
       e.launches += 2;
 
       for (int it = 0; it < iters; ++it) {
-        PP_TRY(pp_k_corr_lookup(corr[0], corr[1], corr[2], corr[3], coords1, lk, 328, M, P, h8, w8, st));
+        {
+          // algorithmic bytes per query pixel: coords 8 B + 4 levels x 10x10 taps x 2 B + 324 outputs x 2 B
+          PPProfScope ps(e, "corr_lookup", (double)M, 0.0, (double)M * (8 + 4 * 100 * 2 + 324 * 2), st);
+          PP_TRY(pp_k_corr_lookup(corr[0], corr[1], corr[2], corr[3], coords1, lk, 328, M, P, h8, w8, st));
+        }
         e.launches++;
         // BasicMotionEncoder (update.py:94-112)
         PP_TRY(PPConvCall(e, "raft.update.convc1", B, h8, w8).in(lk, 328, 0, 328).geom(1, 1, 0, 0)

@@ -102,7 +102,11 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
                    .act(PP_ACT_LRELU, 0.1f).run(st));
         PP_TRY(PPConvCall(e, m + ".offset.3", D, h8, w8).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
         // modulated deformable conv on cat(prop, n2): sample -> GEMM (K = 9*256)
-        PP_TRY(pp_k_dcn_sample(p1, 128, 0, 128, n2, 128, 0, 128, offs, 432, nullptr, 0, 0, 5.0f, cols, D, h8, w8, st));
+        {
+          const double px = (double)D * P;
+          PPProfScope ps(e, "dcn_sample", px, 0.0, px * (256 * 2 + 432 * 2 + 2304 * 2), st);
+          PP_TRY(pp_k_dcn_sample(p1, 128, 0, 128, n2, 128, 0, 128, offs, 432, nullptr, 0, 0, 5.0f, cols, D, h8, w8, st));
+        }
         e.launches++;
         PP_TRY(PPConvCall(e, m + ".dcn", D, h8, w8).in(cols, 2304, 0, 2304).geom(1, 1, 0, 0).out(aligned, 128, 0)
                    .run(st));
@@ -177,15 +181,22 @@ int pp_stage_image_propagate(PPEngine& e, const float* frames, const float* mask
   PP_CUDA_CHECK(cudaMemcpyAsync(bwd + (size_t)(T - 1) * fs, in4 + (size_t)(T - 1) * fs, fs * sizeof(__half),
                                 cudaMemcpyDeviceToDevice, st));
   for (int idx = T - 2; idx >= 0; --idx) {
-    PP_TRY(pp_k_imgprop_step(in4 + idx * fs, bwd + (idx + 1) * fs, bwd + idx * fs, ff + idx * ws, fbk + idx * ws, H, W,
-                             st));
+    {
+      // algorithmic bytes per pixel: cur 8 + propagated gather 8 + out 8 + 2 flows x 4 (32 B/px)
+      PPProfScope ps(e, "imgprop_step", (double)HW, 0.0, (double)HW * 32, st);
+      PP_TRY(pp_k_imgprop_step(in4 + idx * fs, bwd + (idx + 1) * fs, bwd + idx * fs, ff + idx * ws, fbk + idx * ws, H,
+                               W, st));
+    }
     e.launches++;
   }
   // forward pass over the backward pass's outputs: prop flow = flows_backward[idx-1], check = flows_forward[idx-1]
   PP_CUDA_CHECK(cudaMemcpyAsync(fwd, bwd, fs * sizeof(__half), cudaMemcpyDeviceToDevice, st));
   for (int idx = 1; idx < T; ++idx) {
-    PP_TRY(pp_k_imgprop_step(bwd + idx * fs, fwd + (idx - 1) * fs, fwd + idx * fs, fbk + (idx - 1) * ws,
-                             ff + (idx - 1) * ws, H, W, st));
+    {
+      PPProfScope ps(e, "imgprop_step", (double)HW, 0.0, (double)HW * 32, st);
+      PP_TRY(pp_k_imgprop_step(bwd + idx * fs, fwd + (idx - 1) * fs, fwd + idx * fs, fbk + (idx - 1) * ws,
+                               ff + (idx - 1) * ws, H, W, st));
+    }
     e.launches++;
   }
   PP_TRY(pp_k_imgprop_finish(fwd, frames, masks, upd_frames, upd_masks, T, H, W, st));

@@ -40,6 +40,8 @@ _SIGNATURES = {
     "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "pp_launch_count": (_LL, [_VP]),
     "pp_workspace_peak": (_SZ, [_VP]),
+    "pp_profile_enable": (_I, [_VP, _I]),
+    "pp_profile_dump": (_I, [_VP, ctypes.c_char_p, _SZ]),
     "pp_op_conv": (_I, [_VP, _CP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _F, _VP, _VP, _VP]),
     "pp_op_corr_lookup": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _LL, _I, _I, _VP]),
     "pp_op_imgprop_step": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP]),
@@ -368,6 +370,19 @@ class Engine:
     @property
     def workspace_peak(self) -> int:
         return int(self.lib.pp_workspace_peak(self.h))
+
+    def profile_enable(self, on: bool):
+        self._check(self.lib.pp_profile_enable(self.h, int(on)))
+
+    def profile_dump(self):
+        """-> {kernel name: dict(count, ms, rows, flops, bytes)} since profile_enable(True)."""
+        buf = ctypes.create_string_buffer(1 << 20)
+        self._check(self.lib.pp_profile_dump(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms, rows, flops, nbytes = line.split("\t")
+            out[name] = dict(count=int(n), ms=float(ms), rows=float(rows), flops=float(flops), bytes=float(nbytes))
+        return out
 
     # -- single operators (tests / micro-benchmarks)
     def op_conv(self, name, x_nhwc, stride=1, pad=0, dil=1, replicate=False, act=ACT_NONE, slope=0.0, residual=None):

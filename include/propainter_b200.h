@@ -77,6 +77,11 @@ PP_API int pp_composite(pp_handle h, const void* pred_f16, const float* masks_di
 PP_API long long pp_launch_count(pp_handle h);
 PP_API size_t pp_workspace_peak(pp_handle h);
 
+/* Per-kernel timing with CUDA events on the launch stream (bench.py roofline): enable, run, dump a
+ * tab-separated table "name count ms rows flops bytes" aggregated by kernel name. */
+PP_API int pp_profile_enable(pp_handle h, int on);
+PP_API int pp_profile_dump(pp_handle h, char* buf, size_t cap);
+
 /* ---- single-operator entry points (unit tests and micro-benchmarks) ------------------------------------ */
 /* Generic conv / linear through the tcgen05 implicit-GEMM kernel: x NHWC fp16 [N,H,W,cin_g*groups]. */
 PP_API int pp_op_conv(pp_handle h, const char* name, const void* x_f16, int N, int H, int W, int stride, int pad, int dil,
