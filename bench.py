@@ -75,6 +75,12 @@ def synthetic_inputs():
 # ------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (the reference itself is a Python package that cannot travel to the GPU box)
 # ------------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    """Host threads for the CPU arm: all cores up to 32 (beyond that the small 1/8-res convs of the recurrent
+    stages get slower with more threads on the 128-core host; measured in profiles/)."""
+    return min(os.cpu_count() or 1, int(os.environ.get("PP_CPU_THREADS", 32)))
+
+
 def cpu_sample(n_frames=3):
     """Times the CPU oracle on a bounded sample of the same workload: the first `n_frames` frames of the clip with
     the workload's parameters.  Returns (frames/s, seconds)."""
@@ -96,7 +102,7 @@ def cpu_sample(n_frames=3):
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     n = 3
     for _ in range(min(args.warmup, 1)):
@@ -147,6 +153,22 @@ def run_b200(args, rank, world):
     def step():
         uf, um, flows = PI.process_inpainting(models, ft, fm, md, cfg)
         return PI.feature_propagation_device(models.inpaint_model, uf, um, md, flows, orig_dev, cfg)
+
+    def staged():
+        """Same work as step(), with CUDA events between the stages (reported as stage_ms)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        gt = PI.compute_flow(models.raft_model, ft, cfg)
+        ev[1].record()
+        pf = PI.complete_flow(models.flow_model, gt, fm, cfg.subvideo_length)
+        ev[2].record()
+        uf, um = PI.image_propagation(models.inpaint_model, ft, md, pf, cfg)
+        ev[3].record()
+        PI.feature_propagation_device(models.inpaint_model, uf, um, md, pf, orig_dev, cfg)
+        ev[4].record()
+        torch.cuda.synchronize()
+        names = ["raft", "flow_completion", "image_propagation", "generator_windows"]
+        return {n: round(ev[i].elapsed_time(ev[i + 1]), 2) for i, n in enumerate(names)}
 
     def barrier():
         if world > 1:
@@ -199,8 +221,9 @@ def run_b200(args, rank, world):
     d2h = orig_dev.numel()
 
     # ---- per-kernel timing of one extra step (CUDA events on the launch stream) for the roofline
-    roof, extra = None, []
+    roof, extra, stage_ms = None, [], None
     if rank == 0:
+        stage_ms = staged()
         pk = peaks()
         eng.profile_enable(True)
         step()
@@ -230,7 +253,7 @@ def run_b200(args, rank, world):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads()
         torch.set_num_threads(cores)
         v, dt = cpu_sample(3)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -245,7 +268,7 @@ def run_b200(args, rank, world):
                        "roofline_timing": "one extra profiled step after the timed region"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "roofline_other": extra,
-            "cpu_baseline": cpu, "workspace_peak_gb": eng.workspace_peak / 2 ** 30,
+            "stage_ms": stage_ms, "cpu_baseline": cpu, "workspace_peak_gb": eng.workspace_peak / 2 ** 30,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -31,6 +31,34 @@ __device__ __forceinline__ float act_apply(float v, int act, float slope) {
   }
 }
 
+// 16 consecutive fp16 values <-> registers; 2 x 16-byte accesses when the run is complete and aligned
+__device__ __forceinline__ void load16(const __half* src, int nvalid, float (&r)[16]) {
+  if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
+    const __half2* ha = reinterpret_cast<const __half2*>(&a);
+    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fa = __half22float2(ha[i]), fb = __half22float2(hb[i]);
+      r[2 * i] = fa.x; r[2 * i + 1] = fa.y; r[8 + 2 * i] = fb.x; r[8 + 2 * i + 1] = fb.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = i < nvalid ? __half2float(src[i]) : 0.f;
+  }
+}
+__device__ __forceinline__ void store16(__half* dst, int nvalid, const float (&v)[16]) {
+  if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    __align__(16) __half2 h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
+    reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
+  } else {
+    for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(v[i]);
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_constant__ PPConvParams p) {
   using namespace ppx;
   extern __shared__ uint8_t smem_raw[];
@@ -127,23 +155,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_co
         const __half* src = v ? sbase + (long long)(rpix[i] + iy * p.W + ix) * cs : p.seg[0].ptr;
         cp_async16(a_dst + i * (16 * 128), src, v ? 16u : 0u);
       }
-      cp_async_commit();
-      if (kc >= 2) {
-        cp_async_wait<2>();
-        fence_proxy_async();
-        int sp = s - 2; if (sp < 0) sp += S;
-        mbar_arrive(&full_bar[sp]);
-      }
+      // asynchronous arrival: fires when this thread's copies for the stage have landed, so up to `stages`
+      // K chunks are in flight per CTA without any wait in the producer loop
+      cp_async_arrive_noinc(&full_bar[s]);
       if (++s == S) { s = 0; phase ^= 1; }
     }
-    if (num_kc >= 2) {
-      cp_async_wait<1>();
-      fence_proxy_async();
-      mbar_arrive(&full_bar[(num_kc - 2) % S]);
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    mbar_arrive(&full_bar[(num_kc - 1) % S]);
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(accum_bar, 0);
@@ -152,33 +168,47 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_co
     const bool mvalid = m < p.M_total;
     const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
     const long long mrow = m;
+    const int epi = p.epi;
     for (int c0 = 0; c0 < p.BN; c0 += 16) {
       uint32_t raw[16];
       tmem_ld16(t_row + c0, raw);
       tmem_ld_wait();
       const int ng0 = n0 + c0;  // channel within the group
       if (!mvalid || ng0 >= p.Cout_g) continue;
+      const int nvalid = min(16, p.Cout_g - ng0);
+      const bool full = nvalid == 16;
       float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int ng = ng0 + i;
-        float x = __uint_as_float(raw[i]);
-        if (p.bias != nullptr && ng < p.Cout_g) x += __ldg(p.bias + g * p.Cout_g + ng);
-        v[i] = x;
-      }
-      const int nvalid = min(16, p.Cout_g - ng0);
-      if (p.epi == PP_EPI_STD) {
-        const __half* res = p.aux0 ? p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0 : nullptr;
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+      if (p.bias != nullptr) {
+        const float* bp = p.bias + g * p.Cout_g + ng0;
+        if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x = act_apply(v[i], p.act1, p.slope) * p.scale;
-          if (res != nullptr && i < nvalid) x += __half2float(res[i]);
-          v[i] = act_apply(x, p.act2, p.slope);
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + i);
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
+        } else {
+          for (int i = 0; i < nvalid; ++i) v[i] += __ldg(bp + i);
+        }
+      }
+      if (epi == PP_EPI_STD) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act1, p.slope) * p.scale;
+        if (p.aux0 != nullptr) {
+          float r[16];
+          load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += r[i];
+        }
+        if (p.act2 != PP_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act2, p.slope);
         }
         const long long o = mrow * p.out_cstride + p.out_coff + (long long)g * p.out_gstep + ng0;
         if (p.out_fp32) {
           float* dst = reinterpret_cast<float*>(p.out) + o;
-          if (nvalid == 16 && ((o & 3) == 0)) {
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -186,36 +216,29 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_co
             for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
           }
         } else {
-          __half* dst = reinterpret_cast<__half*>(p.out) + o;
-          if (nvalid == 16 && ((o & 7) == 0)) {
-            __align__(16) __half2 h[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
-            reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
-          } else {
-            for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(v[i]);
-          }
+          store16(reinterpret_cast<__half*>(p.out) + o, nvalid, v);
         }
-      } else if (p.epi == PP_EPI_GRU_ZR) {
+      } else if (epi == PP_EPI_GRU_ZR) {
         const int half_c = p.Cout_g >> 1;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = ppx::sigmoidf_(v[i]);
         if (ng0 < half_c) {
-          __half* dst = reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0;
-          for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(ppx::sigmoidf_(v[i]));
+          store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
         } else {
           const int c = ng0 - half_c;
-          const __half* h = p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c;
-          __half* dst = p.out2 + mrow * p.out2_cstride + p.out2_coff + c;
-          for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(ppx::sigmoidf_(v[i]) * __half2float(h[i]));
+          float h[16];
+          load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, h);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= h[i];
+          store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, v);
         }
       } else {  // PP_EPI_GRU_H
-        const __half* h = p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0;
-        const __half* z = p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0;
-        __half* dst = reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0;
-        for (int i = 0; i < nvalid; ++i) {
-          const float zz = __half2float(z[i]);
-          dst[i] = __float2half_rn((1.f - zz) * __half2float(h[i]) + zz * tanhf(v[i]));
-        }
+        float h[16], z[16];
+        load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, h);
+        load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, z);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * tanhf(v[i]);
+        store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
       }
     }
   } else if (warp == 4) {

@@ -19,6 +19,7 @@ _LIB = None
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libpropainter_b200.so")
 
+MAX_BN = 128
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH, ACT_GELU = range(6)
 
 _VP, _I, _F, _LL, _SZ, _CP = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t,
@@ -76,10 +77,20 @@ def exported_symbols():
 
 
 def choose_bn(cout: int) -> Tuple[int, int]:
-    """N-tile of the tcgen05 GEMM: fewest tiles of <= 256 columns, each a multiple of 16."""
-    n_tiles = (cout + 255) // 256
-    bn = ((cout + n_tiles - 1) // n_tiles + 15) // 16 * 16
-    return bn, bn * n_tiles
+    """N-tile of the tcgen05 GEMM: tiles of <= MAX_BN columns (multiple of 16) with the least padding.
+
+    MAX_BN = 128 keeps a pipeline stage at 32 KiB so two CTAs co-reside on an SM (one's epilogue overlaps the
+    other's main loop) and two 128-column accumulators fit in TMEM."""
+    best = None
+    t0 = (cout + MAX_BN - 1) // MAX_BN
+    for n_tiles in (t0, t0 + 1):
+        bn = ((cout + n_tiles - 1) // n_tiles + 15) // 16 * 16
+        if bn > MAX_BN:
+            continue
+        cand = (bn * n_tiles, n_tiles, bn)
+        if best is None or cand < best:
+            best = cand
+    return best[2], best[0]
 
 
 def pack_conv_weight(w: torch.Tensor, groups: int = 1, cin_map=None):
