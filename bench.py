@@ -10,6 +10,7 @@ pre-processing, H2D, D2H of the result inside the timed region).  Weights are se
 the real architectures (no network in this environment).
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -202,7 +203,8 @@ def run_b200(args, rank, world):
     node = ProPainterInpaint()
     img_host, mask_host = image.pin_memory(), mask.pin_memory()
     def e2e_step():
-        frames, _, _ = node.propainter_inpainting(img_host, mask_host, WIDTH, HEIGHT, **PARAMS)
+        with contextlib.redirect_stdout(sys.stderr):   # the node prints progress; stdout carries only the JSON line
+            frames, _, _ = node.propainter_inpainting(img_host, mask_host, WIDTH, HEIGHT, **PARAMS)
         return frames
     e2e_step()
     barrier()

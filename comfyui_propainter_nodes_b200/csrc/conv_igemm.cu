@@ -1,13 +1,13 @@
 // tcgen05 implicit-GEMM convolution for sm_100a.  See conv_igemm.cuh for the contract.
 //
-// CTA = 192 threads, one 128 x BN output tile:
-//   warps 0-3  im2col producers: 16-byte cp.async gathers into a 128B-swizzled K-major A tile,
-//              then the epilogue (TMEM -> registers -> bias/activation/fusions -> global)
-//   warp  4    one elected lane issues tcgen05.mma (M=128, N=BN, K=16 x4 per 64-wide K chunk)
-//   warp  5    TMEM allocation; one lane streams the pre-swizzled weight tile with a single
-//              cp.async.bulk (TMA engine) per stage
-// Pipeline: `stages` smem slots, full/empty mbarriers; the accumulator (128 lanes x BN fp32 columns)
-// lives in tensor memory until the epilogue.
+// Persistent CTA (one per SM, 448 threads) looping over 128 x BN output tiles:
+//   warps 0-3   epilogue: tcgen05.ld of the finished accumulator -> bias/activation/fusions -> global
+//   warps 4-11  im2col producers: 16-byte cp.async gathers into a 128B-swizzled K-major A tile
+//   warp  12    one lane issues tcgen05.mma (M=128, N=BN, K=16 x4 per 64-wide K chunk)
+//   warp  13    TMEM allocation; one lane streams the pre-swizzled weight tile with a single
+//               cp.async.bulk (TMA engine) per stage
+// Pipelines: `stages` smem slots (full/empty mbarriers) that keep filling across tile boundaries, and two
+// TMEM accumulators (acc_full/acc_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "conv_igemm.cuh"
 
 namespace {
@@ -15,10 +15,13 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int NUM_PRODUCERS = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPILOGUE = 128;   // warps 0-3
+constexpr int NUM_PRODUCERS = 256;  // warps 4-11
+constexpr int WARP_MMA = 12;
+constexpr int WARP_TMA = 13;
+constexpr int NUM_THREADS = 448;
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 100 * 1024;
+constexpr int SMEM_BUDGET = 200 * 1024;
 
 __device__ __forceinline__ float act_apply(float v, int act, float slope) {
   switch (act) {
@@ -59,7 +62,7 @@ __device__ __forceinline__ void store16(__half* dst, int nvalid, const float (&v
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_constant__ PPConvParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid_constant__ PPConvParams p) {
   using namespace ppx;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -70,29 +73,35 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_co
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* accum_bar = empty_bar + MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + MAX_STAGES;   // [2] accumulator ready for the epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2] accumulator drained, MMA may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * p.BN;
-  const int g = blockIdx.z;
   const int num_kc = p.num_kc;
+  const int m_tiles = (p.M_total + BM - 1) / BM;
+  const int n_tiles = p.Cout_g_pad / p.BN;
+  const int total_tiles = m_tiles * n_tiles * p.groups;
 
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+  // two accumulator buffers of `acc_cols` TMEM columns each
+  uint32_t acc_cols = 32;
+  while (acc_cols < (uint32_t)p.BN) acc_cols <<= 1;
+  const uint32_t tmem_cols = acc_cols * 2;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], NUM_PRODUCERS + 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], NUM_EPILOGUE);
+    }
     mbar_fence_init();
   }
-  if (warp == 5) {
+  if (warp == WARP_TMA) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
@@ -102,192 +111,222 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_igemm_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ------------------------------------------------------------------ im2col producers
-    const int j = tid & 7;    // 16-byte chunk inside the 128-byte K row
-    const int rb = tid >> 3;  // rows rb, rb+16, ..., rb+112
-    int rpix[8], riy[8], rix[8];
-    uint32_t rvalid = 0;
+    // ------------------------------------------------------------------ epilogue warps (TMEM lanes 32*warp..)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int epi = p.epi;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_idx = tile % n_tiles;
+      const int rest = tile / n_tiles;
+      const int m0 = (rest % m_tiles) * BM;
+      const int g = rest / m_tiles;
+      const int n0 = n_idx * p.BN;
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const int m = m0 + warp * 32 + lane;
+      const bool mvalid = m < p.M_total;
+      const uint32_t t_row = tmem_base + lane_base + buf * acc_cols;
+      const long long mrow = m;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(t_row + c0, raw);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.BN) {  // last read of this accumulator: hand the buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        const int ng0 = n0 + c0;  // channel within the group
+        if (!mvalid || ng0 >= p.Cout_g) continue;
+        const int nvalid = min(16, p.Cout_g - ng0);
+        const bool full = nvalid == 16;
+        float v[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + rb + 16 * i;
-      if (m < p.M_total) {
-        const int ox = m % p.OW;
-        const int t = m / p.OW;
-        const int oy = t % p.OH;
-        const int img = t / p.OH;
-        rpix[i] = img * p.H * p.W;
-        riy[i] = oy * p.sh - p.ph;
-        rix[i] = ox * p.sw - p.pw;
-        rvalid |= 1u << i;
-      } else {
-        rpix[i] = 0; riy[i] = 0; rix[i] = 0;
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+        if (p.bias != nullptr) {
+          const float* bp = p.bias + g * p.Cout_g + ng0;
+          if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+          } else {
+            for (int i = 0; i < nvalid; ++i) v[i] += __ldg(bp + i);
+          }
+        }
+        if (epi == PP_EPI_STD) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act1, p.slope) * p.scale;
+          if (p.aux0 != nullptr) {
+            float r[16];
+            load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += r[i];
+          }
+          if (p.act2 != PP_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act2, p.slope);
+          }
+          const long long o = mrow * p.out_cstride + p.out_coff + (long long)g * p.out_gstep + ng0;
+          if (p.out_fp32) {
+            float* dst = reinterpret_cast<float*>(p.out) + o;
+            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+            }
+          } else {
+            store16(reinterpret_cast<__half*>(p.out) + o, nvalid, v);
+          }
+        } else if (epi == PP_EPI_GRU_ZR) {
+          const int half_c = p.Cout_g >> 1;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = ppx::sigmoidf_(v[i]);
+          if (ng0 < half_c) {
+            store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
+          } else {
+            const int c = ng0 - half_c;
+            float h[16];
+            load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, h);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= h[i];
+            store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, v);
+          }
+        } else {  // PP_EPI_GRU_H
+          float h[16], z[16];
+          load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, h);
+          load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, z);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * tanhf(v[i]);
+          store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
+        }
       }
     }
+  } else if (warp < WARP_MMA) {
+    // ------------------------------------------------------------------ im2col producers (8 warps)
+    const int ptid = tid - 128;
+    const int j = ptid & 7;    // 16-byte chunk inside the 128-byte K row
+    const int rb = ptid >> 3;  // rows rb, rb+32, rb+64, rb+96
     const uint32_t a_off = rb * 128 + ((j ^ (rb & 7)) << 4);
     int s = 0;
     uint32_t phase = 0;
-    for (int kc = 0; kc < num_kc; ++kc) {
-      mbar_wait(&empty_bar[s], phase ^ 1);
-      const int k = kc * BK + j * 8;
-      const bool kvalid = k < p.K_total;
-      const int tap = k / p.Cin;
-      const int ci = k - tap * p.Cin;
-      const int ky = tap / p.kw;
-      const int kx = tap - ky * p.kw;
-      int q = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int rest = tile / n_tiles;
+      const int m0 = (rest % m_tiles) * BM;
+      const int g = rest / m_tiles;
+      int rpix[4], riy[4], rix[4];
+      uint32_t rvalid = 0;
 #pragma unroll
-      for (int t = 1; t < 4; ++t)
-        if (t < p.nseg && ci >= p.seg[t].cbegin) q = t;
-      const __half* sbase = p.seg[q].ptr + p.seg[q].coff + g * p.seg[q].gstep + (ci - p.seg[q].cbegin);
-      const long long cs = p.seg[q].cstride;
-      const int dy = ky * p.dh, dx = kx * p.dw;
-      const uint32_t a_dst = smem_u32(smem + s * stage_bytes) + a_off;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int iy = riy[i] + dy, ix = rix[i] + dx;
-        bool v = kvalid && ((rvalid >> i) & 1u);
-        if (p.pad_replicate) {
-          iy = min(max(iy, 0), p.H - 1);
-          ix = min(max(ix, 0), p.W - 1);
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + rb + 32 * i;
+        if (m < p.M_total) {
+          const int ox = m % p.OW;
+          const int t = m / p.OW;
+          const int oy = t % p.OH;
+          const int img = t / p.OH;
+          rpix[i] = img * p.H * p.W;
+          riy[i] = oy * p.sh - p.ph;
+          rix[i] = ox * p.sw - p.pw;
+          rvalid |= 1u << i;
         } else {
-          v = v && ((unsigned)iy < (unsigned)p.H) && ((unsigned)ix < (unsigned)p.W);
-        }
-        const __half* src = v ? sbase + (long long)(rpix[i] + iy * p.W + ix) * cs : p.seg[0].ptr;
-        cp_async16(a_dst + i * (16 * 128), src, v ? 16u : 0u);
-      }
-      // asynchronous arrival: fires when this thread's copies for the stage have landed, so up to `stages`
-      // K chunks are in flight per CTA without any wait in the producer loop
-      cp_async_arrive_noinc(&full_bar[s]);
-      if (++s == S) { s = 0; phase ^= 1; }
-    }
-
-    // ------------------------------------------------------------------ epilogue
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-    const bool mvalid = m < p.M_total;
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const long long mrow = m;
-    const int epi = p.epi;
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      uint32_t raw[16];
-      tmem_ld16(t_row + c0, raw);
-      tmem_ld_wait();
-      const int ng0 = n0 + c0;  // channel within the group
-      if (!mvalid || ng0 >= p.Cout_g) continue;
-      const int nvalid = min(16, p.Cout_g - ng0);
-      const bool full = nvalid == 16;
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-      if (p.bias != nullptr) {
-        const float* bp = p.bias + g * p.Cout_g + ng0;
-        if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + i);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-          }
-        } else {
-          for (int i = 0; i < nvalid; ++i) v[i] += __ldg(bp + i);
+          rpix[i] = 0; riy[i] = 0; rix[i] = 0;
         }
       }
-      if (epi == PP_EPI_STD) {
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        const int k = kc * BK + j * 8;
+        const bool kvalid = k < p.K_total;
+        const int tap = k / p.Cin;
+        const int ci = k - tap * p.Cin;
+        const int ky = tap / p.kw;
+        const int kx = tap - ky * p.kw;
+        int q = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act1, p.slope) * p.scale;
-        if (p.aux0 != nullptr) {
-          float r[16];
-          load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, r);
+        for (int t = 1; t < 4; ++t)
+          if (t < p.nseg && ci >= p.seg[t].cbegin) q = t;
+        const __half* sbase = p.seg[q].ptr + p.seg[q].coff + g * p.seg[q].gstep + (ci - p.seg[q].cbegin);
+        const long long cs = p.seg[q].cstride;
+        const int dy = ky * p.dh, dx = kx * p.dw;
+        const uint32_t a_dst = smem_u32(smem + s * stage_bytes) + a_off;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += r[i];
-        }
-        if (p.act2 != PP_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act2, p.slope);
-        }
-        const long long o = mrow * p.out_cstride + p.out_coff + (long long)g * p.out_gstep + ng0;
-        if (p.out_fp32) {
-          float* dst = reinterpret_cast<float*>(p.out) + o;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 4; ++i) {
+          int iy = riy[i] + dy, ix = rix[i] + dx;
+          bool v = kvalid && ((rvalid >> i) & 1u);
+          if (p.pad_replicate) {
+            iy = min(max(iy, 0), p.H - 1);
+            ix = min(max(ix, 0), p.W - 1);
           } else {
-            for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+            v = v && ((unsigned)iy < (unsigned)p.H) && ((unsigned)ix < (unsigned)p.W);
           }
-        } else {
-          store16(reinterpret_cast<__half*>(p.out) + o, nvalid, v);
+          const __half* src = v ? sbase + (long long)(rpix[i] + iy * p.W + ix) * cs : p.seg[0].ptr;
+          cp_async16(a_dst + i * (32 * 128), src, v ? 16u : 0u);
         }
-      } else if (epi == PP_EPI_GRU_ZR) {
-        const int half_c = p.Cout_g >> 1;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = ppx::sigmoidf_(v[i]);
-        if (ng0 < half_c) {
-          store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
-        } else {
-          const int c = ng0 - half_c;
-          float h[16];
-          load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, h);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= h[i];
-          store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, v);
-        }
-      } else {  // PP_EPI_GRU_H
-        float h[16], z[16];
-        load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, h);
-        load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, z);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * tanhf(v[i]);
-        store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
+        // asynchronous arrival: fires when this thread's copies for the stage have landed, so up to `stages`
+        // K chunks (across tile boundaries) are in flight without any wait in the producer loop
+        cp_async_arrive_noinc(&full_bar[s]);
+        if (++s == S) { s = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == WARP_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(BM, p.BN);
-      int s = 0;
+      int s = 0, it = 0;
       uint32_t phase = 0;
-      for (int kc = 0; kc < num_kc; ++kc) {
-        mbar_wait(&full_bar[s], phase);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        fence_proxy_async();
-        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint64_t adesc = umma_desc_sw128_kmajor(a_addr);
-        const uint64_t bdesc = umma_desc_sw128_kmajor(a_addr + A_STAGE_BYTES);
+        const uint32_t d_addr = tmem_base + buf * acc_cols;
+        for (int kc = 0; kc < num_kc; ++kc) {
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          fence_proxy_async();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t adesc = umma_desc_sw128_kmajor(a_addr);
+          const uint64_t bdesc = umma_desc_sw128_kmajor(a_addr + A_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
-        if (++s == S) { s = 0; phase ^= 1; }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(d_addr, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (++s == S) { s = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(accum_bar);
     }
   } else {
     // ------------------------------------------------------------------ weight-tile loader (TMA bulk copy)
     if (lane == 0) {
-      const __half* wsrc = p.wpacked + ((long long)g * num_kc * p.Cout_g_pad + n0) * BK;
       int s = 0;
       uint32_t phase = 0;
-      for (int kc = 0; kc < num_kc; ++kc) {
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
-        bulk_g2s(smem_u32(smem + s * stage_bytes + A_STAGE_BYTES), wsrc + (long long)kc * p.Cout_g_pad * BK,
-                 (uint32_t)b_stage_bytes, &full_bar[s]);
-        if (++s == S) { s = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles) * p.BN;
+        const int g = tile / (n_tiles * m_tiles);
+        const __half* wsrc = p.wpacked + ((long long)g * num_kc * p.Cout_g_pad + n0) * BK;
+        for (int kc = 0; kc < num_kc; ++kc) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
+          bulk_g2s(smem_u32(smem + s * stage_bytes + A_STAGE_BYTES), wsrc + (long long)kc * p.Cout_g_pad * BK,
+                   (uint32_t)b_stage_bytes, &full_bar[s]);
+          if (++s == S) { s = 0; phase ^= 1; }
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == WARP_TMA) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 }  // namespace
 
 int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
   PPConvParams p = pin;
-  PP_REQUIRE(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "conv: BN=%d must be a multiple of 16 in [16,256]", p.BN);
+  PP_REQUIRE(p.BN >= 16 && p.BN <= 128 && p.BN % 16 == 0, "conv: BN=%d must be a multiple of 16 in [16,128]", p.BN);
   PP_REQUIRE(p.Cout_g_pad % p.BN == 0, "conv: Cout_g_pad=%d not a multiple of BN=%d", p.Cout_g_pad, p.BN);
   PP_REQUIRE(p.Cin % 8 == 0, "conv: Cin=%d must be a multiple of 8", p.Cin);
   PP_REQUIRE(p.nseg >= 1 && p.nseg <= 4, "conv: nseg=%d", p.nseg);
@@ -303,18 +342,22 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
   p.num_kc = pp_ceil_div(p.K_total, BK);
   p.M_total = p.N * p.OH * p.OW;
   if (p.M_total <= 0) return PP_OK;
+  PP_REQUIRE(p.BN <= 128, "conv: BN=%d > 128 (two accumulators must fit the 512 TMEM columns)", p.BN);
   const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
   int stages = SMEM_BUDGET / stage_bytes;
-  if (stages > 6) stages = 6;
-  if (stages < 3) stages = 3;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PP_CUDA_CHECK(cudaGetDevice(&dev));
+    PP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   }
-  dim3 grid(pp_ceil_div(p.M_total, BM), p.Cout_g_pad / p.BN, p.groups);
+  const long long total_tiles = (long long)pp_ceil_div(p.M_total, BM) * (p.Cout_g_pad / p.BN) * p.groups;
+  PP_REQUIRE(total_tiles < (1LL << 31), "conv: too many tiles");
+  const int grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
   conv_igemm_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;

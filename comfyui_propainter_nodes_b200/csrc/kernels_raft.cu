@@ -105,9 +105,7 @@ __global__ void corr_pool(const __half* __restrict__ src, __half* __restrict__ d
 // ------------------------------------------------------------------------------------------------
 // Correlation lookup (CorrBlock.__call__, corr.py:29-50; bilinear_sampler, RAFT/utils/utils.py:66-80).
 // Output channel c = l*81 + i*9 + j samples level l at (x/2^l + (i-4), y/2^l + (j-4)), bilinear,
-// zeros outside, align_corners=True.  One thread per output channel: consecutive threads write
-// consecutive channels (coalesced 2-byte stores); the 10x10 tap window of a query pixel is shared by
-// its 81 threads per level through L1.
+// zeros outside, align_corners=True.
 // ------------------------------------------------------------------------------------------------
 struct CorrLevels {
   const __half* p[4];
