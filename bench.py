@@ -206,17 +206,19 @@ def run_b200(args, rank, world):
         with contextlib.redirect_stdout(sys.stderr):   # the node prints progress; stdout carries only the JSON line
             frames, _, _ = node.propainter_inpainting(img_host, mask_host, WIDTH, HEIGHT, **PARAMS)
         return frames
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
-    for _ in range(n_e2e):
-        res = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * T_FRAMES / float(e2e_s.item())
+    e2e_value = None
+    if not args.no_e2e:
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_value = world * T_FRAMES / float(e2e_s.item())
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = ft.numel() * 4 + fm.numel() * 4 + md.numel() * 4 + orig_dev.numel()
@@ -224,7 +226,7 @@ def run_b200(args, rank, world):
 
     # ---- per-kernel timing of one extra step (CUDA events on the launch stream) for the roofline
     roof, extra, stage_ms = None, [], None
-    if rank == 0:
+    if rank == 0 and not args.no_profile:
         stage_ms = staged()
         pk = peaks()
         eng.profile_enable(True)
@@ -250,6 +252,9 @@ def run_b200(args, rank, world):
             v = prof["attention"]
             extra.append({"kernel": "window_attention (mma.sync, flops upper bound: all windows masked)", "bound": "tensor",
                           "ms": v["ms"], "launches": v["count"]})
+        if args.profile_out:
+            with open(args.profile_out, "w") as fh:
+                json.dump({"stage_ms": stage_ms, "kernels": prof}, fh, indent=1, sort_keys=True)
         top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]
         extra.append({"top_by_time_ms": {k: round(v["ms"], 3) for k, v in top}, "profiled_step_kernel_ms": all_ms})
 
@@ -283,6 +288,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the node-level end-to-end leg (profiling runs)")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel timed extra step")
+    ap.add_argument("--profile-out", default=None, help="write the full per-kernel table (JSON) here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

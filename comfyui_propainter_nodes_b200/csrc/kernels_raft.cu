@@ -111,33 +111,53 @@ struct CorrLevels {
   const __half* p[4];
 };
 
-__global__ void corr_lookup(CorrLevels lv, const float* __restrict__ coords, __half* __restrict__ out, int out_cs,
-                            long long nq, int P, int h8, int w8) {
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= nq * out_cs) return;
-  const int c = idx % out_cs;
-  const long long q = idx / out_cs;
-  if (c >= 324) { out[idx] = __float2half_rn(0.f); return; }
-  const int l = c / 81, r = c - l * 81;
-  const int i = r / 9, j = r - i * 9;
+// One warp per query pixel.  For a given (pixel, level) all 81 outputs share the same bilinear fractions
+// (the window offsets are integers), so the warp stages the 10x10 tap window of each level in shared memory
+// once (400 taps, zero outside the map) and every lane then blends 4 staged taps per output:
+//   out[l*81 + i*9 + j] = bilerp(T_l[j..j+1][i..i+1])      (i moves x, j moves y -- the meshgrid quirk)
+// Global traffic per pixel = the algorithmic 8 B coords + 400 taps + 324 outputs; stores are contiguous.
+constexpr int LOOKUP_WARPS = 8;
+
+__global__ void __launch_bounds__(LOOKUP_WARPS * 32) corr_lookup(CorrLevels lv, const float* __restrict__ coords,
+                                                                 __half* __restrict__ out, int out_cs, long long nq,
+                                                                 int h8, int w8) {
+  __shared__ float taps[LOOKUP_WARPS][4][104];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q = (long long)blockIdx.x * LOOKUP_WARPS + warp;
+  if (q >= nq) return;
   const float cx = coords[q * 2], cy = coords[q * 2 + 1];
-  const float inv = 1.f / (float)(1 << l);
-  const int h = h8 >> l, w = w8 >> l;
-  // the reference normalises to [-1,1] and grid_sample maps back; both are exact inverses up to fp32 rounding
-  const float x = cx * inv + (float)(i - 4), y = cy * inv + (float)(j - 4);
-  const float fx = floorf(x), fy = floorf(y);
-  const int x0 = (int)fx, y0 = (int)fy;
-  const float ax = x - fx, ay = y - fy;
-  const __half* m = lv.p[l] + q * (long long)(h * w);
-  float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
-  const bool xin0 = x0 >= 0 && x0 < w, xin1 = x0 + 1 >= 0 && x0 + 1 < w;
-  const bool yin0 = y0 >= 0 && y0 < h, yin1 = y0 + 1 >= 0 && y0 + 1 < h;
-  if (yin0 && xin0) v00 = __half2float(m[y0 * w + x0]);
-  if (yin0 && xin1) v01 = __half2float(m[y0 * w + x0 + 1]);
-  if (yin1 && xin0) v10 = __half2float(m[(y0 + 1) * w + x0]);
-  if (yin1 && xin1) v11 = __half2float(m[(y0 + 1) * w + x0 + 1]);
-  const float val = (1.f - ay) * ((1.f - ax) * v00 + ax * v01) + ay * ((1.f - ax) * v10 + ax * v11);
-  out[idx] = __float2half_rn(val);
+  float ax[4], ay[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float inv = 1.f / (float)(1 << l);
+    const int h = h8 >> l, w = w8 >> l;
+    const float x = cx * inv, y = cy * inv;
+    const float fx = floorf(x), fy = floorf(y);
+    ax[l] = x - fx; ay[l] = y - fy;
+    const int x0 = (int)fx - 4, y0 = (int)fy - 4;
+    const __half* m = lv.p[l] + q * (long long)(h * w);
+    for (int t = lane; t < 100; t += 32) {
+      const int ty = t / 10, tx = t - ty * 10;
+      const int yy = y0 + ty, xx = x0 + tx;
+      float v = 0.f;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __half2float(m[yy * w + xx]);
+      taps[warp][l][t] = v;
+    }
+  }
+  __syncwarp();
+  __half* o = out + q * out_cs;
+  for (int c = lane; c < out_cs; c += 32) {
+    float val = 0.f;
+    if (c < 324) {
+      const int l = c / 81, r = c - l * 81;
+      const int i = r / 9, j = r - i * 9;
+      const float* T = taps[warp][l];
+      const float a = ax[l], b = ay[l];
+      val = (1.f - b) * ((1.f - a) * T[j * 10 + i] + a * T[j * 10 + i + 1]) +
+            b * ((1.f - a) * T[(j + 1) * 10 + i] + a * T[(j + 1) * 10 + i + 1]);
+    }
+    o[c] = __float2half_rn(val);
+  }
 }
 
 // cnet output -> GRU state: h = tanh(c[:, :128]) into hx[:, 0:128], inp = relu(c[:, 128:]) into hx[:, 128:256]
@@ -248,8 +268,9 @@ int pp_k_corr_lookup(const __half* l0, const __half* l1, const __half* l2, const
   PP_REQUIRE(out_cs >= 324, "corr_lookup: out_cs=%d < 324", out_cs);
   CorrLevels lv;
   lv.p[0] = l0; lv.p[1] = l1; lv.p[2] = l2; lv.p[3] = l3;
-  const long long total = nq * out_cs;
-  corr_lookup<<<nblocks(total), TPB, 0, st>>>(lv, coords, out, out_cs, nq, P, h8, w8);
+  (void)P;
+  corr_lookup<<<(unsigned)((nq + LOOKUP_WARPS - 1) / LOOKUP_WARPS), LOOKUP_WARPS * 32, 0, st>>>(lv, coords, out, out_cs,
+                                                                                              nq, h8, w8);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }
