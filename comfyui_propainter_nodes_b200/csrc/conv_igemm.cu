@@ -23,20 +23,33 @@ constexpr int NUM_THREADS = 448;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
-__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+template <int ACT>
+__device__ __forceinline__ void act16_t(float (&v)[16], float slope) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (ACT == PP_ACT_RELU) v[i] = fmaxf(v[i], 0.f);
+    else if (ACT == PP_ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+    else if (ACT == PP_ACT_SIGMOID) v[i] = ppx::sigmoidf_(v[i]);
+    else if (ACT == PP_ACT_TANH) v[i] = tanhf(v[i]);
+    else if (ACT == PP_ACT_GELU) v[i] = ppx::gelu_erf(v[i]);
+  }
+}
+// one (uniform) branch per 16 values instead of one per value
+__device__ __forceinline__ void act16(float (&v)[16], int act, float slope) {
   switch (act) {
-    case PP_ACT_RELU: return fmaxf(v, 0.f);
-    case PP_ACT_LRELU: return v > 0.f ? v : v * slope;
-    case PP_ACT_SIGMOID: return ppx::sigmoidf_(v);
-    case PP_ACT_TANH: return tanhf(v);
-    case PP_ACT_GELU: return ppx::gelu_erf(v);
-    default: return v;
+    case PP_ACT_RELU: act16_t<PP_ACT_RELU>(v, slope); break;
+    case PP_ACT_LRELU: act16_t<PP_ACT_LRELU>(v, slope); break;
+    case PP_ACT_SIGMOID: act16_t<PP_ACT_SIGMOID>(v, slope); break;
+    case PP_ACT_TANH: act16_t<PP_ACT_TANH>(v, slope); break;
+    case PP_ACT_GELU: act16_t<PP_ACT_GELU>(v, slope); break;
+    default: break;
   }
 }
 
-// 16 consecutive fp16 values <-> registers; 2 x 16-byte accesses when the run is complete and aligned
-__device__ __forceinline__ void load16(const __half* src, int nvalid, float (&r)[16]) {
-  if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+// 16 consecutive fp16 values <-> registers.  `vec` (uniform per launch, checked on the host) says that full
+// runs are 16-byte aligned, so they move as 2 x 16-byte accesses; partial runs take the scalar tail.
+__device__ __forceinline__ void load16(const __half* src, int nvalid, bool vec, float (&r)[16]) {
+  if (vec && nvalid == 16) {
     const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
     const __half2* ha = reinterpret_cast<const __half2*>(&a);
     const __half2* hb = reinterpret_cast<const __half2*>(&b);
@@ -50,15 +63,17 @@ __device__ __forceinline__ void load16(const __half* src, int nvalid, float (&r)
     for (int i = 0; i < 16; ++i) r[i] = i < nvalid ? __half2float(src[i]) : 0.f;
   }
 }
-__device__ __forceinline__ void store16(__half* dst, int nvalid, const float (&v)[16]) {
-  if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+__device__ __forceinline__ void store16(__half* dst, int nvalid, bool vec, const float (&v)[16]) {
+  if (vec && nvalid == 16) {
     __align__(16) __half2 h[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
     reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
   } else {
-    for (int i = 0; i < nvalid; ++i) dst[i] = __float2half_rn(v[i]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = __float2half_rn(v[i]);
   }
 }
 
@@ -114,6 +129,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
     // ------------------------------------------------------------------ epilogue warps (TMEM lanes 32*warp..)
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const int epi = p.epi;
+    const bool vec = p.vec_ok != 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_idx = tile % n_tiles;
@@ -139,69 +155,72 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
         const int ng0 = n0 + c0;  // channel within the group
         if (!mvalid || ng0 >= p.Cout_g) continue;
         const int nvalid = min(16, p.Cout_g - ng0);
-        const bool full = nvalid == 16;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
         if (p.bias != nullptr) {
           const float* bp = p.bias + g * p.Cout_g + ng0;
-          if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+          if (vec && nvalid == 16) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + i);
               v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
             }
           } else {
-            for (int i = 0; i < nvalid; ++i) v[i] += __ldg(bp + i);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) v[i] += __ldg(bp + i);
           }
         }
         if (epi == PP_EPI_STD) {
+          act16(v, p.act1, p.slope);
+          if (p.scale != 1.f) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act1, p.slope) * p.scale;
+            for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+          }
           if (p.aux0 != nullptr) {
             float r[16];
-            load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, r);
+            load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, r);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += r[i];
           }
-          if (p.act2 != PP_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = act_apply(v[i], p.act2, p.slope);
-          }
+          act16(v, p.act2, p.slope);
           const long long o = mrow * p.out_cstride + p.out_coff + (long long)g * p.out_gstep + ng0;
           if (p.out_fp32) {
             float* dst = reinterpret_cast<float*>(p.out) + o;
-            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            if (vec && nvalid == 16) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             } else {
-              for (int i = 0; i < nvalid; ++i) dst[i] = v[i];
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) dst[i] = v[i];
             }
           } else {
-            store16(reinterpret_cast<__half*>(p.out) + o, nvalid, v);
+            store16(reinterpret_cast<__half*>(p.out) + o, nvalid, vec, v);
           }
         } else if (epi == PP_EPI_GRU_ZR) {
           const int half_c = p.Cout_g >> 1;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = ppx::sigmoidf_(v[i]);
+          act16_t<PP_ACT_SIGMOID>(v, 0.f);
           if (ng0 < half_c) {
-            store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
+            store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v);
           } else {
             const int c = ng0 - half_c;
             float h[16];
-            load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, h);
+            load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, vec, h);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= h[i];
-            store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, v);
+            store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, vec, v);
           }
         } else {  // PP_EPI_GRU_H
           float h[16], z[16];
-          load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, h);
-          load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, z);
+          load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, h);
+          load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, vec, z);
+          act16_t<PP_ACT_TANH>(v, 0.f);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * tanhf(v[i]);
-          store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, v);
+          for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * v[i];
+          store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v);
         }
       }
     }
@@ -235,14 +254,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
           rpix[i] = 0; riy[i] = 0; rix[i] = 0;
         }
       }
+      // this thread's position inside the K range: channel ci of tap (ky, kx); advances by 64 per chunk
+      int k = j * 8;
+      int tap0 = k / p.Cin;
+      int ci = k - tap0 * p.Cin;
+      int ky = tap0 / p.kw;
+      int kx = tap0 - ky * p.kw;
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&empty_bar[s], phase ^ 1);
-        const int k = kc * BK + j * 8;
         const bool kvalid = k < p.K_total;
-        const int tap = k / p.Cin;
-        const int ci = k - tap * p.Cin;
-        const int ky = tap / p.kw;
-        const int kx = tap - ky * p.kw;
         int q = 0;
 #pragma unroll
         for (int t = 1; t < 4; ++t)
@@ -263,6 +283,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
           }
           const __half* src = v ? sbase + (long long)(rpix[i] + iy * p.W + ix) * cs : p.seg[0].ptr;
           cp_async16(a_dst + i * (32 * 128), src, v ? 16u : 0u);
+        }
+        k += BK;
+        ci += BK;
+        while (ci >= p.Cin) {
+          ci -= p.Cin;
+          if (++kx == p.kw) { kx = 0; ++ky; }
         }
         // asynchronous arrival: fires when this thread's copies for the stage have landed, so up to `stages`
         // K chunks (across tile boundaries) are in flight without any wait in the producer loop
@@ -342,6 +368,17 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
   p.num_kc = pp_ceil_div(p.K_total, BK);
   p.M_total = p.N * p.OH * p.OW;
   if (p.M_total <= 0) return PP_OK;
+  {
+    const int esz = p.out_fp32 ? 4 : 2, per16 = 16 / esz;
+    auto al = [](const void* ptr, long long cs, long long co, long long gs, int per) {
+      return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cs % per == 0 && co % per == 0 && gs % per == 0);
+    };
+    bool ok = al(p.out, p.out_cstride, p.out_coff, p.out_gstep, per16) && al(p.aux0, p.aux0_cstride, p.aux0_coff, 0, 8) &&
+              al(p.aux1, p.aux1_cstride, p.aux1_coff, 0, 8) && al(p.out2, p.out2_cstride, p.out2_coff, 0, 8);
+    if (p.bias != nullptr) ok = ok && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (p.groups == 1 || p.Cout_g % 4 == 0);
+    if (p.epi == PP_EPI_GRU_ZR) ok = ok && ((p.Cout_g >> 1) % 16 == 0);
+    p.vec_ok = ok ? 1 : 0;
+  }
   PP_REQUIRE(p.BN <= 128, "conv: BN=%d > 128 (two accumulators must fit the 512 TMEM columns)", p.BN);
   const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
   int stages = SMEM_BUDGET / stage_bytes;

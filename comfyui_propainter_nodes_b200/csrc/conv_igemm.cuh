@@ -41,6 +41,7 @@ struct PPConvParams {
   const float* bias;      // [groups*Cout_g] or nullptr
   int Cout_g, Cout_g_pad, BN, groups;
   int stages;
+  int vec_ok;             // set by the launcher: every epilogue pointer/stride allows 16-byte accesses on full runs
   // epilogue
   int epi, act1, act2;
   float slope, scale;
