@@ -47,7 +47,7 @@ int pp_register_conv(pp_handle h, const char* name, const void* w, const float* 
                      int bn, int cin_g, int kh, int kw, int groups) {
   PP_HANDLE(h);
   PP_REQUIRE(name != nullptr && w != nullptr, "pp_register_conv: null argument");
-  PP_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 128 && cout_g_pad % bn == 0 && cout_g <= cout_g_pad && cin_g % 8 == 0,
+  PP_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256 && cout_g_pad % bn == 0 && cout_g <= cout_g_pad && cin_g % 8 == 0,
              "pp_register_conv(%s): invalid packing (cout_g=%d pad=%d bn=%d cin_g=%d)", name, cout_g, cout_g_pad, bn,
              cin_g);
   PPPackedConv c;

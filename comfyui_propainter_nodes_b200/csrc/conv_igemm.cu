@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
 
 int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
   PPConvParams p = pin;
-  PP_REQUIRE(p.BN >= 16 && p.BN <= 128 && p.BN % 16 == 0, "conv: BN=%d must be a multiple of 16 in [16,128]", p.BN);
+  PP_REQUIRE(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "conv: BN=%d must be a multiple of 16 in [16,256]", p.BN);
   PP_REQUIRE(p.Cout_g_pad % p.BN == 0, "conv: Cout_g_pad=%d not a multiple of BN=%d", p.Cout_g_pad, p.BN);
   PP_REQUIRE(p.Cin % 8 == 0, "conv: Cin=%d must be a multiple of 8", p.Cin);
   PP_REQUIRE(p.nseg >= 1 && p.nseg <= 4, "conv: nseg=%d", p.nseg);
@@ -379,7 +379,6 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
     if (p.epi == PP_EPI_GRU_ZR) ok = ok && ((p.Cout_g >> 1) % 16 == 0);
     p.vec_ok = ok ? 1 : 0;
   }
-  PP_REQUIRE(p.BN <= 128, "conv: BN=%d > 128 (two accumulators must fit the 512 TMEM columns)", p.BN);
   const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;

@@ -103,7 +103,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
   __half *fmap, *cmap, *fpack;
   int P_pad;
   {
-    const int ntile = pp_ceil_div(P, 128);
+    const int ntile = pp_ceil_div(P, 256);
     const int bn = ((pp_ceil_div(P, ntile) + 15) / 16) * 16;
     P_pad = bn * ntile;
   }
@@ -144,7 +144,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
   int max_pairs = (int)(avail * 9 / 10 / per_pair);
   PP_REQUIRE(max_pairs >= 1, "raft: workspace too small for one frame pair (%zu bytes needed)", per_pair);
   const int npairs = T - 1;
-  const int bn_corr = P_pad / pp_ceil_div(P, 128);
+  const int bn_corr = P_pad / pp_ceil_div(P, 256);
 
   for (int dir = 0; dir < 2; ++dir) {
     for (int b0 = 0; b0 < npairs; b0 += max_pairs) {

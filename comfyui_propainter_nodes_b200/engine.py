@@ -19,7 +19,7 @@ _LIB = None
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libpropainter_b200.so")
 
-MAX_BN = 128
+MAX_BN = 256
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH, ACT_GELU = range(6)
 
 _VP, _I, _F, _LL, _SZ, _CP = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_size_t,
@@ -79,8 +79,8 @@ def exported_symbols():
 def choose_bn(cout: int) -> Tuple[int, int]:
     """N-tile of the tcgen05 GEMM: tiles of <= MAX_BN columns (multiple of 16) with the least padding.
 
-    MAX_BN = 128 keeps a pipeline stage at 32 KiB so two CTAs co-reside on an SM (one's epilogue overlaps the
-    other's main loop) and two 128-column accumulators fit in TMEM."""
+    MAX_BN = 256: two 256-column fp32 accumulators fill the 512 TMEM columns of the persistent CTA, and a wide
+    N tile halves the im2col (A operand) traffic per output for the Cout >= 256 layers."""
     best = None
     t0 = (cout + MAX_BN - 1) // MAX_BN
     for n_tiles in (t0, t0 + 1):
