@@ -25,9 +25,11 @@ struct AttnParams {
   const __half* q; const __half* k; const __half* v; int qkv_cs;  // padded token grid [t][nh*nw][cs]
   const __half* pk; const __half* pv; int pool_cs;                // pooled tokens [t][n_pool][cs]
   __half* out; int out_cs;                                        // unpadded grid [t][gh*gw][cs]
-  const int* win_flags;                                           // [n_win] 1 = masked window
+  const int* win_flags;                                           // [n_sliding][n_win] 1 = masked window
   const int* ring_idx;                                            // [n_win][193] token index in padded grid
-  int t, gh, gw, nh, nw, nww, n_pool, parity, n_tind;
+  const int* sw_frame_off;                                        // [n_sliding] first frame of each sliding window
+  const int* sw_t;                                                // [n_sliding] frames in each sliding window
+  int n_win, gh, gw, nh, nw, nww, n_pool, parity;
   float scale_log2;
 };
 
@@ -59,20 +61,24 @@ __global__ void __launch_bounds__(NT) window_attention(const AttnParams p) {
   uint8_t* sK = smem + BQ * 256;         // 2 stages x 64 x 256 B
   uint8_t* sV = sK + 2 * BKEY * 256;     // 2 stages
   const int win = blockIdx.y >> 2, head = blockIdx.y & 3;
-  const bool masked = p.win_flags[win] != 0;
+  const int sw = blockIdx.z;                 // sliding window of the batch
+  const int t = p.sw_t[sw];
+  const int frame_base = p.sw_frame_off[sw];
+  const int n_tind = (t - p.parity + 1) / 2;
+  const bool masked = p.win_flags[sw * p.n_win + win] != 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   int nq, nk, q_frame0;
   if (masked) {
-    nq = p.t * WIN_TOK;
+    nq = t * WIN_TOK;
     if ((int)blockIdx.x * BQ >= nq) return;
-    nk = p.n_tind * (RING + p.n_pool);
-    q_frame0 = 0;
+    nk = n_tind * (RING + p.n_pool);
+    q_frame0 = frame_base;
   } else {
-    if ((int)blockIdx.x >= p.t) return;
+    if ((int)blockIdx.x >= t) return;
     nq = WIN_TOK;
     nk = WIN_TOK;
-    q_frame0 = blockIdx.x;
+    q_frame0 = frame_base + blockIdx.x;
   }
   const int q0 = masked ? blockIdx.x * BQ : 0;
   const int* ring = p.ring_idx + win * RING;
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(NT) window_attention(const AttnParams p) {
       if (j < nk) {
         nbytes = 16;
         int fr, w;
-        if (masked) { const int fi = j / kpf; w = j - fi * kpf; fr = p.parity + 2 * fi; }
+        if (masked) { const int fi = j / kpf; w = j - fi * kpf; fr = frame_base + p.parity + 2 * fi; }
         else { fr = q_frame0; w = j; }
         if (w < RING) {
           const long long off = ((long long)fr * ntok + ring[w]) * p.qkv_cs + head * D + ch * 8;
@@ -222,18 +228,19 @@ __global__ void __launch_bounds__(NT) window_attention(const AttnParams p) {
 }  // namespace
 
 int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs, const __half* pk, const __half* pv,
-                   int pool_cs, __half* out, int out_cs, const int* win_flags, const int* ring_idx, int t, int gh,
-                   int gw, int nh, int nw, int n_pool, int t_parity, cudaStream_t st) {
+                   int pool_cs, __half* out, int out_cs, const int* win_flags, const int* ring_idx,
+                   const int* sw_frame_off, const int* sw_t, int n_sliding, int t_max, int gh, int gw, int nh, int nw,
+                   int n_pool, int t_parity, cudaStream_t st) {
   PP_REQUIRE(nh % 5 == 0 && nw % 9 == 0, "attention: padded grid %dx%d is not a multiple of the 5x9 window", nh, nw);
   AttnParams p;
   p.q = q; p.k = k; p.v = v; p.qkv_cs = qkv_cs; p.pk = pk; p.pv = pv; p.pool_cs = pool_cs;
   p.out = out; p.out_cs = out_cs; p.win_flags = win_flags; p.ring_idx = ring_idx;
-  p.t = t; p.gh = gh; p.gw = gw; p.nh = nh; p.nw = nw; p.nww = nw / 9; p.n_pool = n_pool; p.parity = t_parity;
-  p.n_tind = (t - t_parity + 1) / 2;
+  p.sw_frame_off = sw_frame_off; p.sw_t = sw_t;
+  p.gh = gh; p.gw = gw; p.nh = nh; p.nw = nw; p.nww = nw / 9; p.n_pool = n_pool; p.parity = t_parity;
+  p.n_win = (nh / 5) * (nw / 9);
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
-  const int n_win = (nh / 5) * (nw / 9);
-  const int qtiles_masked = pp_ceil_div(t * WIN_TOK, BQ);
-  dim3 grid(qtiles_masked > t ? qtiles_masked : t, n_win * 4);
+  const int qtiles_masked = pp_ceil_div(t_max * WIN_TOK, BQ);
+  dim3 grid(qtiles_masked > t_max ? qtiles_masked : t_max, p.n_win * 4, n_sliding);
   const size_t smem = (size_t)(BQ + 4 * BKEY) * 256;
   static bool attr_set = false;
   if (!attr_set) {

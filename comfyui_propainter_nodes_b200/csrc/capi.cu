@@ -103,6 +103,13 @@ int pp_gen_window(pp_handle h, const int* frame_ids, int t, int l_t, void* pred_
   return pp_stage_gen_window(e, frame_ids, t, l_t, static_cast<__half*>(pred_f16), as_stream(stream));
 }
 
+int pp_gen_run(pp_handle h, const int* frame_ids, const int* win_t, const int* win_lt, int n_windows, void* pred_f16,
+               void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(frame_ids && win_t && win_lt && pred_f16, "pp_gen_run: null pointer");
+  return pp_stage_gen_run(e, frame_ids, win_t, win_lt, n_windows, static_cast<__half*>(pred_f16), as_stream(stream));
+}
+
 int pp_gen_end(pp_handle h) {
   PP_HANDLE(h);
   return pp_stage_gen_end(e);
@@ -201,8 +208,13 @@ int pp_op_attention(pp_handle h, const void* qkv_f16, const void* pkv_f16, void*
                                 as_stream(stream)));
   const __half* qkv = static_cast<const __half*>(qkv_f16);
   const __half* pkv = static_cast<const __half*>(pkv_f16);
+  int meta_host[2] = {0, t};
+  int* meta_dev;
+  PP_TRY(pp_alloc(e, &meta_dev, 2, "attention meta"));
+  PP_CUDA_CHECK(cudaMemcpyAsync(meta_dev, meta_host, sizeof(meta_host), cudaMemcpyHostToDevice, as_stream(stream)));
   int r = pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, static_cast<__half*>(out_f16), 512,
-                         win_flags_dev, ring_dev, t, gh, gw, nh, nw, n_pool, parity, as_stream(stream));
+                         win_flags_dev, ring_dev, meta_dev, meta_dev + 1, 1, t, gh, gw, nh, nw, n_pool, parity,
+                         as_stream(stream));
   PP_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
   e.arena.release(mark);
   e.launches++;

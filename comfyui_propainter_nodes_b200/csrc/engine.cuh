@@ -129,4 +129,6 @@ int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, 
                  const float* flows_f, const float* flows_b, int T, int H, int W, cudaStream_t st);
 int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __half* pred /*[l_t][H][W][8]*/,
                   cudaStream_t st);
+int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const int* win_lt, int n_windows,
+                     __half* pred /*[sum l_t][H][W][4]*/, cudaStream_t st);
 int pp_stage_gen_end(PPEngine& e);

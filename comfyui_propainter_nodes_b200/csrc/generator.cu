@@ -144,99 +144,180 @@ int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, 
   return PP_OK;
 }
 
-int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __half* pred, cudaStream_t st) {
+// All sliding windows of a clip in one pass.  Windows are independent (the reference walks them in a Python
+// loop), so every stage is batched across them: feature propagation steps run on all windows of equal local
+// length at once, the transformer sees the concatenated token rows of all windows, and the decoder runs on all
+// local frames.  frame_ids = concatenation of every window's [local frames..., reference frames...].
+int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const int* win_lt, int n_sw, __half* pred,
+                     cudaStream_t st) {
   PPEngine::GenSession& g = e.gen;
   PP_REQUIRE(g.active, "generator: pp_gen_begin was not called");
-  PP_REQUIRE(l_t >= 1 && l_t <= t, "generator: l_t=%d t=%d", l_t, t);
-  for (int i = 0; i < t; ++i) PP_REQUIRE(frame_ids[i] >= 0 && frame_ids[i] < g.T, "generator: frame id out of range");
-  for (int i = 1; i < l_t; ++i)
-    PP_REQUIRE(frame_ids[i] == frame_ids[0] + i, "generator: local frames must be consecutive");
+  PP_REQUIRE(n_sw >= 1, "generator: no windows");
   const int H = g.H, W = g.W, h4 = H / 4, w4 = W / 4, h2 = H / 2, w2 = W / 2;
   const long long P4 = (long long)h4 * w4;
   const int gh = g.gh, gw = g.gw, nh = g.nh, nw = g.nw, ng = gh * gw, np = g.ph * g.pw;
-  const int f0 = frame_ids[0];
-  const size_t mark0 = e.arena.mark();
+  const int n_win = (nh / WIN_H) * (nw / WIN_W);
   const size_t fsz = (size_t)P4 * 128;
 
-  // ---- learnable bidirectional feature propagation on the local frames (propainter.py:118-231) ------
-  const __half* x_local = g.enc + (size_t)f0 * fsz;
-  const __half* mask2 = g.mask_in4 + (size_t)f0 * P4 * 8;
-  __half *ob, *of, *cond, *o1, *o2, *offs, *cols, *aligned, *bb, *encw;
-  PP_TRY(pp_alloc(e, &ob, (size_t)l_t * fsz, "featprop backward"));
-  PP_TRY(pp_alloc(e, &of, (size_t)l_t * fsz, "featprop forward"));
-  PP_TRY(pp_alloc(e, &cond, (size_t)P4 * 264, "featprop cond"));
-  PP_TRY(pp_alloc(e, &o1, fsz, "featprop o1"));
-  PP_TRY(pp_alloc(e, &o2, fsz, "featprop o2"));
-  PP_TRY(pp_alloc(e, &offs, (size_t)P4 * 432, "featprop offsets"));
-  PP_TRY(pp_alloc(e, &cols, (size_t)P4 * 1152, "featprop dcn columns"));
-  PP_TRY(pp_alloc(e, &aligned, fsz, "featprop aligned"));
-  PP_TRY(pp_alloc(e, &bb, (size_t)l_t * fsz, "featprop tmp"));
-  PP_TRY(pp_alloc(e, &encw, (size_t)t * fsz, "window features"));
-  for (int mod = 0; mod < 2; ++mod) {
-    const std::string m = mod == 0 ? "gen.fp.backward_1" : "gen.fp.forward_1";
-    const __half* src = mod == 0 ? x_local : ob;  // the forward pass consumes the backward outputs
-    __half* dst = mod == 0 ? ob : of;
-    for (int i = 0; i < l_t; ++i) {
-      const int idx = mod == 0 ? l_t - 1 - i : i;
-      const __half* cur = src + (size_t)idx * fsz;
-      const __half* m2 = mask2 + (size_t)idx * P4 * 8;
-      const __half* prop = cur;
-      if (i > 0) {
-        const int prev = mod == 0 ? idx + 1 : idx - 1;
-        const int fi = mod == 0 ? idx : idx - 1;  // flow index
-        const __half* fprop = (mod == 0 ? g.flows_f4 : g.flows_b4) + (size_t)(f0 + fi) * P4 * 2;
-        const __half* fchk = (mod == 0 ? g.flows_b4 : g.flows_f4) + (size_t)(f0 + fi) * P4 * 2;
-        const __half* pprev = dst + (size_t)prev * fsz;
-        {
-          PPProfScope ps(e, "featprop_warp", (double)P4, 0.0, (double)P4 * (128 * 2 * 2 + 264 * 2 + 8 + 16), st);
-          PP_TRY(pp_k_featprop_cond(cur, 128, pprev, 128, fprop, fchk, m2, 8, cond, 264, h4, w4, 128, st));
-        }
-        e.launches++;
-        PP_TRY(PPConvCall(e, m + ".offset.0", 1, h4, w4).in(cond, 264, 0, 264).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
-        PP_TRY(PPConvCall(e, m + ".offset.1", 1, h4, w4).in(o1, 128, 0, 128).out(o2, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
-        PP_TRY(PPConvCall(e, m + ".offset.2", 1, h4, w4).in(o2, 128, 0, 128).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
-        PP_TRY(PPConvCall(e, m + ".offset.3", 1, h4, w4).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
-        // offsets = 3*tanh(.) + flow (dy,dx) (propainter.py:66-68); flow sits at cond[:, 256:258]
-        {
-          PPProfScope ps(e, "dcn_sample", (double)P4, 0.0, (double)P4 * (128 * 2 + 432 * 2 + 1152 * 2), st);
-          PP_TRY(pp_k_dcn_sample(pprev, 128, 0, 128, nullptr, 0, 0, 0, offs, 432, cond, 264, 256, 3.0f, cols, 1, h4, w4, st));
-        }
-        e.launches++;
-        PP_TRY(PPConvCall(e, m + ".dcn", 1, h4, w4).in(cols, 1152, 0, 1152).geom(1, 1, 0, 0).out(aligned, 128, 0).run(st));
-        prop = aligned;
-      }
-      // feat_prop = feat_prop + backbone(cat(cur, feat_prop, mask_current))
-      PP_TRY(PPConvCall(e, m + ".backbone.0", 1, h4, w4).in(cur, 128, 0, 128).in(prop, 128, 0, 128).in(m2, 8, 0, 8)
-                 .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
-      PP_TRY(PPConvCall(e, m + ".backbone.1", 1, h4, w4).in(bb, 128, 0, 128).out(dst + (size_t)idx * fsz, 128, 0)
-                 .residual(prop, 128, 0).run(st));
-    }
+  // ---- schedule bookkeeping (host) ----------------------------------------------------------------
+  std::vector<int> foff(n_sw + 1, 0), loff(n_sw + 1, 0), f0(n_sw);
+  int t_max = 0;
+  for (int w = 0; w < n_sw; ++w) {
+    const int t = win_t[w], lt = win_lt[w];
+    PP_REQUIRE(lt >= 1 && lt <= t, "generator: window %d has l_t=%d t=%d", w, lt, t);
+    const int* ids = frame_ids + foff[w];
+    for (int i = 0; i < t; ++i) PP_REQUIRE(ids[i] >= 0 && ids[i] < g.T, "generator: frame id out of range");
+    for (int i = 1; i < lt; ++i) PP_REQUIRE(ids[i] == ids[0] + i, "generator: local frames must be consecutive");
+    f0[w] = ids[0];
+    foff[w + 1] = foff[w] + t;
+    loff[w + 1] = loff[w] + lt;
+    if (t > t_max) t_max = t;
   }
-  // fuse(cat(out_b, out_f, mask)) + x  -> local part of the window features
-  PP_TRY(PPConvCall(e, "gen.fp.fuse.0", l_t, h4, w4).in(ob, 128, 0, 128).in(of, 128, 0, 128).in(mask2, 8, 0, 8)
-             .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
-  PP_TRY(PPConvCall(e, "gen.fp.fuse.1", l_t, h4, w4).in(bb, 128, 0, 128).out(encw, 128, 0)
-             .residual(x_local, 128, 0).run(st));
-  for (int i = l_t; i < t; ++i)
-    PP_CUDA_CHECK(cudaMemcpyAsync(encw + (size_t)i * fsz, g.enc + (size_t)frame_ids[i] * fsz, fsz * sizeof(__half),
+  const int TT = foff[n_sw], LT = loff[n_sw];  // all frames / all local frames of the batch
+  // groups of windows with equal local length (uniform step count)
+  std::vector<int> lts;
+  for (int w = 0; w < n_sw; ++w) {
+    bool seen = false;
+    for (int v : lts) seen = seen || v == win_lt[w];
+    if (!seen) lts.push_back(win_lt[w]);
+  }
+  // one index table for every gather of this call
+  std::vector<int> tab;
+  auto push = [&](const std::vector<int>& v) { const int o = (int)tab.size(); tab.insert(tab.end(), v.begin(), v.end()); return o; };
+  struct Group { int L, n; std::vector<int> wins; int o_x, o_ff, o_scatter_src, o_scatter_dst; };
+  std::vector<Group> groups;
+  for (int L : lts) {
+    Group G; G.L = L;
+    for (int w = 0; w < n_sw; ++w) if (win_lt[w] == L) G.wins.push_back(w);
+    G.n = (int)G.wins.size();
+    std::vector<int> ix, ifl;
+    for (int k = 0; k < L; ++k) for (int w : G.wins) ix.push_back(f0[w] + k);          // [k][w] <- session frame
+    for (int k = 0; k < L - 1; ++k) for (int w : G.wins) ifl.push_back(f0[w] + k);     // [k][w] <- session flow
+    G.o_x = push(ix); G.o_ff = push(ifl);
+    groups.push_back(G);
+  }
+  // refs: window-major slot <- session frame
+  std::vector<int> ref_dst, ref_src, loc_rows, sw_f0(f0), sw_lt(win_lt, win_lt + n_sw), sw_t(win_t, win_t + n_sw),
+      sw_foff(foff.begin(), foff.end() - 1);
+  for (int w = 0; w < n_sw; ++w) {
+    for (int i = win_lt[w]; i < win_t[w]; ++i) { ref_dst.push_back(foff[w] + i); ref_src.push_back(frame_ids[foff[w] + i]); }
+    for (int k = 0; k < win_lt[w]; ++k) loc_rows.push_back(foff[w] + k);                // local frame -> window-major slot
+  }
+  const int o_ref_src = push(ref_src), o_loc = push(loc_rows), o_f0 = push(sw_f0), o_lt = push(sw_lt), o_t = push(sw_t),
+            o_foff = push(sw_foff);
+  (void)ref_dst;
+
+  const size_t mark0 = e.arena.mark();
+  int* tab_dev;
+  PP_TRY(pp_alloc(e, &tab_dev, tab.size(), "gather table"));
+  PP_CUDA_CHECK(cudaMemcpyAsync(tab_dev, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+
+  __half* encw;  // window-major features [TT][P4][128]
+  PP_TRY(pp_alloc(e, &encw, (size_t)TT * fsz, "window features"));
+
+  // ---- learnable bidirectional feature propagation (propainter.py:118-231), per group of equal l_t -------
+  for (const Group& G : groups) {
+    const size_t mg = e.arena.mark();
+    const int L = G.L, n = G.n;
+    const size_t slab = (size_t)n * fsz;            // one frame index k over the group's windows
+    __half *X, *M2, *FF, *FB, *ob, *of, *cond, *o1, *o2, *offs, *cols, *aligned, *bb;
+    PP_TRY(pp_alloc(e, &X, (size_t)L * slab, "featprop x"));
+    PP_TRY(pp_alloc(e, &M2, (size_t)L * n * P4 * 8, "featprop masks"));
+    PP_TRY(pp_alloc(e, &FF, (size_t)(L > 1 ? L - 1 : 1) * n * P4 * 2, "featprop flows f"));
+    PP_TRY(pp_alloc(e, &FB, (size_t)(L > 1 ? L - 1 : 1) * n * P4 * 2, "featprop flows b"));
+    PP_TRY(pp_alloc(e, &ob, (size_t)L * slab, "featprop backward"));
+    PP_TRY(pp_alloc(e, &of, (size_t)L * slab, "featprop forward"));
+    PP_TRY(pp_alloc(e, &cond, (size_t)n * P4 * 264, "featprop cond"));
+    PP_TRY(pp_alloc(e, &o1, slab, "featprop o1"));
+    PP_TRY(pp_alloc(e, &o2, slab, "featprop o2"));
+    PP_TRY(pp_alloc(e, &offs, (size_t)n * P4 * 432, "featprop offsets"));
+    PP_TRY(pp_alloc(e, &cols, (size_t)n * P4 * 1152, "featprop dcn columns"));
+    PP_TRY(pp_alloc(e, &aligned, slab, "featprop aligned"));
+    PP_TRY(pp_alloc(e, &bb, (size_t)L * slab, "featprop tmp"));
+    PP_TRY(pp_k_gather_blocks(X, g.enc, tab_dev + G.o_x, (long long)L * n, fsz * 2, st));
+    PP_TRY(pp_k_gather_blocks(M2, g.mask_in4, tab_dev + G.o_x, (long long)L * n, P4 * 8 * 2, st));
+    PP_TRY(pp_k_gather_blocks(FF, g.flows_f4, tab_dev + G.o_ff, (long long)(L - 1) * n, P4 * 2 * 2, st));
+    PP_TRY(pp_k_gather_blocks(FB, g.flows_b4, tab_dev + G.o_ff, (long long)(L - 1) * n, P4 * 2 * 2, st));
+    e.launches += 4;
+    const size_t mslab = (size_t)n * P4 * 8, wslab = (size_t)n * P4 * 2;
+    for (int mod = 0; mod < 2; ++mod) {
+      const std::string m = mod == 0 ? "gen.fp.backward_1" : "gen.fp.forward_1";
+      const __half* src = mod == 0 ? X : ob;  // the forward pass consumes the backward outputs
+      __half* dst = mod == 0 ? ob : of;
+      for (int i = 0; i < L; ++i) {
+        const int idx = mod == 0 ? L - 1 - i : i;
+        const __half* cur = src + (size_t)idx * slab;
+        const __half* m2 = M2 + (size_t)idx * mslab;
+        const __half* prop = cur;
+        if (i > 0) {
+          const int prev = mod == 0 ? idx + 1 : idx - 1;
+          const int fi = mod == 0 ? idx : idx - 1;  // flow index
+          const __half* fprop = (mod == 0 ? FF : FB) + (size_t)fi * wslab;
+          const __half* fchk = (mod == 0 ? FB : FF) + (size_t)fi * wslab;
+          const __half* pprev = dst + (size_t)prev * slab;
+          {
+            const double px = (double)n * P4;
+            PPProfScope ps(e, "featprop_warp", px, 0.0, px * (128 * 2 * 2 + 264 * 2 + 8 + 16), st);
+            PP_TRY(pp_k_featprop_cond(cur, 128, pprev, 128, fprop, fchk, m2, 8, cond, 264, n, h4, w4, 128, st));
+          }
+          e.launches++;
+          PP_TRY(PPConvCall(e, m + ".offset.0", n, h4, w4).in(cond, 264, 0, 264).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
+          PP_TRY(PPConvCall(e, m + ".offset.1", n, h4, w4).in(o1, 128, 0, 128).out(o2, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
+          PP_TRY(PPConvCall(e, m + ".offset.2", n, h4, w4).in(o2, 128, 0, 128).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
+          PP_TRY(PPConvCall(e, m + ".offset.3", n, h4, w4).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
+          // offsets = 3*tanh(.) + flow (dy,dx) (propainter.py:66-68); flow sits at cond[:, 256:258]
+          {
+            const double px = (double)n * P4;
+            PPProfScope ps(e, "dcn_sample", px, 0.0, px * (128 * 2 + 432 * 2 + 1152 * 2), st);
+            PP_TRY(pp_k_dcn_sample(pprev, 128, 0, 128, nullptr, 0, 0, 0, offs, 432, cond, 264, 256, 3.0f, cols, n, h4, w4, st));
+          }
+          e.launches++;
+          PP_TRY(PPConvCall(e, m + ".dcn", n, h4, w4).in(cols, 1152, 0, 1152).geom(1, 1, 0, 0).out(aligned, 128, 0).run(st));
+          prop = aligned;
+        }
+        // feat_prop = feat_prop + backbone(cat(cur, feat_prop, mask_current))
+        PP_TRY(PPConvCall(e, m + ".backbone.0", n, h4, w4).in(cur, 128, 0, 128).in(prop, 128, 0, 128).in(m2, 8, 0, 8)
+                   .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+        PP_TRY(PPConvCall(e, m + ".backbone.1", n, h4, w4).in(bb, 128, 0, 128).out(dst + (size_t)idx * slab, 128, 0)
+                   .residual(prop, 128, 0).run(st));
+      }
+    }
+    // fuse(cat(out_b, out_f, mask)) + x over every (k, window) frame of the group; result reuses `ob`
+    PP_TRY(PPConvCall(e, "gen.fp.fuse.0", L * n, h4, w4).in(ob, 128, 0, 128).in(of, 128, 0, 128).in(M2, 8, 0, 8)
+               .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+    PP_TRY(PPConvCall(e, "gen.fp.fuse.1", L * n, h4, w4).in(bb, 128, 0, 128).out(of, 128, 0).residual(X, 128, 0).run(st));
+    // scatter [k][w] -> window-major slots (async D2D copies: n*L small, frame sized)
+    for (int k = 0; k < L; ++k)
+      for (int j = 0; j < n; ++j)
+        PP_CUDA_CHECK(cudaMemcpyAsync(encw + (size_t)(foff[G.wins[j]] + k) * fsz, of + ((size_t)k * n + j) * fsz,
+                                      fsz * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    e.arena.release(mg);
+  }
+  // reference frames straight from the encoder cache
+  for (size_t r = 0; r < ref_src.size(); ++r)
+    PP_CUDA_CHECK(cudaMemcpyAsync(encw + (size_t)ref_dst[r] * fsz, g.enc + (size_t)ref_src[r] * fsz, fsz * sizeof(__half),
                                   cudaMemcpyDeviceToDevice, st));
+  (void)o_ref_src;
 
   // ---- SoftSplit: unfold(7,3,3) + Linear == 7x7 stride-3 conv (sparse_transformer.py:8-36) ------------
-  const long long rows = (long long)t * ng, rows_pad = (long long)t * nh * nw;
+  const long long rows = (long long)TT * ng, rows_pad = (long long)TT * nh * nw;
   __half *x, *xn, *qkv, *pooled, *pkv, *att, *y, *f1, *img40;
+  int* flags;
   PP_TRY(pp_alloc(e, &x, (size_t)rows * 512, "tokens"));
   PP_TRY(pp_alloc(e, &xn, (size_t)rows_pad * 512, "normed tokens"));
   PP_TRY(pp_alloc(e, &qkv, (size_t)rows_pad * 1536, "qkv"));
-  PP_TRY(pp_alloc(e, &pooled, (size_t)t * np * 512, "pooled tokens"));
-  PP_TRY(pp_alloc(e, &pkv, (size_t)t * np * 1024, "pooled kv"));
+  PP_TRY(pp_alloc(e, &pooled, (size_t)TT * np * 512, "pooled tokens"));
+  PP_TRY(pp_alloc(e, &pkv, (size_t)TT * np * 1024, "pooled kv"));
   PP_TRY(pp_alloc(e, &att, (size_t)rows * 512, "attention out"));
   PP_TRY(pp_alloc(e, &y, (size_t)rows * 512, "normed tokens 2"));
   PP_TRY(pp_alloc(e, &f1, (size_t)rows * 1960, "ffn hidden"));
-  PP_TRY(pp_alloc(e, &img40, (size_t)t * P4 * 40, "ffn folded"));
-  PP_TRY(PPConvCall(e, "gen.ss", t, h4, w4).in(encw, 128, 0, 128).geom(3, 3, 3, 3).out(x, 512, 0).run(st));
+  PP_TRY(pp_alloc(e, &img40, (size_t)TT * P4 * 40, "ffn folded"));
+  PP_TRY(pp_alloc(e, &flags, (size_t)n_sw * n_win, "window flags"));
+  PP_TRY(PPConvCall(e, "gen.ss", TT, h4, w4).in(encw, 128, 0, 128).geom(3, 3, 3, 3).out(x, 512, 0).run(st));
   if (nh != gh || nw != gw) PP_CUDA_CHECK(cudaMemsetAsync(xn, 0, (size_t)rows_pad * 512 * sizeof(__half), st));
   // window dispatch flags from the local frames' original masks (propainter.py:417-428)
-  PP_TRY(pp_k_window_flags(mask2, 8, 0, l_t, h4, w4, gh, gw, nh / WIN_H, nw / WIN_W, g.win_flags, st));
+  PP_TRY(pp_k_window_flags(g.mask_in4, 8, 0, tab_dev + o_f0, tab_dev + o_lt, n_sw, h4, w4, gh, gw, nh / WIN_H, nw / WIN_W,
+                           flags, st));
   e.launches++;
 
   for (int blk = 0; blk < 8; ++blk) {
@@ -250,49 +331,72 @@ int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __hal
     PP_TRY(pp_get_tensor(e, b + "pool.bias", &pbs));
     PP_TRY(pp_k_layernorm(x, (const float*)g1, (const float*)b1, xn, rows, gh, gw, nh, nw, st));
     PP_TRY(PPConvCall(e, b + "qkv", 1, 1, (int)rows_pad).in(xn, 512, 0, 512).out(qkv, 1536, 0).run(st));
-    PP_TRY(pp_k_pool_tokens(xn, (const float*)pwt, (const float*)pbs, pooled, t, nh, nw, g.ph, g.pw, 512, st));
-    PP_TRY(PPConvCall(e, b + "kv", 1, 1, t * np).in(pooled, 512, 0, 512).out(pkv, 1024, 0).run(st));
+    PP_TRY(pp_k_pool_tokens(xn, (const float*)pwt, (const float*)pbs, pooled, TT, nh, nw, g.ph, g.pw, 512, st));
+    PP_TRY(PPConvCall(e, b + "kv", 1, 1, TT * np).in(pooled, 512, 0, 512).out(pkv, 1024, 0).run(st));
     {
-      // flops if every window were masked (upper bound; the masked fraction is data dependent)
-      const double nti = (t - blk % 2 + 1) / 2, nkeys = nti * (193 + np);
-      PPProfScope ps(e, "attention", (double)rows_pad, 4.0 * rows_pad * nkeys * 512, 0.0, st);
-      PP_TRY(pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, att, 512, g.win_flags, g.ring_idx,
-                            t, gh, gw, nh, nw, np, blk % 2, st));
+      // flops if every 5x9 window were masked (upper bound; the masked fraction is data dependent)
+      double fl = 0;
+      for (int w = 0; w < n_sw; ++w)
+        fl += 4.0 * win_t[w] * nh * nw * ((win_t[w] - blk % 2 + 1) / 2) * (193 + np) * 512;
+      PPProfScope ps(e, "attention", (double)rows_pad, fl, 0.0, st);
+      PP_TRY(pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, att, 512, flags, g.ring_idx,
+                            tab_dev + o_foff, tab_dev + o_t, n_sw, t_max, gh, gw, nh, nw, np, blk % 2, st));
     }
     PP_TRY(PPConvCall(e, b + "proj", 1, 1, (int)rows).in(att, 512, 0, 512).out(x, 512, 0).residual(x, 512, 0).run(st));
     PP_TRY(pp_k_layernorm(x, (const float*)g2, (const float*)b2, y, rows, gh, gw, gh, gw, st));
     // FusionFeedForward (sparse_transformer.py:67-123): fc1 -> fold/normalise/(unfold) -> GELU -> fc2
     PP_TRY(PPConvCall(e, b + "fc1", 1, 1, (int)rows).in(y, 512, 0, 512).out(f1, 1960, 0).run(st));
     {
-      PPProfScope ps(e, "fold_ffn", (double)rows, 0.0, (double)rows * 1960 * 2 + (double)t * P4 * 40 * 2, st);
-      PP_TRY(pp_k_fold(f1, 1960, img40, t, h4, w4, 40, gh, gw, 1, 1, st));
+      PPProfScope ps(e, "fold_ffn", (double)rows, 0.0, (double)rows * 1960 * 2 + (double)TT * P4 * 40 * 2, st);
+      PP_TRY(pp_k_fold(f1, 1960, img40, TT, h4, w4, 40, gh, gw, 1, 1, st));
     }
-    PP_TRY(PPConvCall(e, b + "fc2", t, h4, w4).in(img40, 40, 0, 40).geom(3, 3, 3, 3).out(x, 512, 0)
+    PP_TRY(PPConvCall(e, b + "fc2", TT, h4, w4).in(img40, 40, 0, 40).geom(3, 3, 3, 3).out(x, 512, 0)
                .residual(x, 512, 0).run(st));
     e.launches += 5;
   }
 
   // ---- SoftComp on the local frames only (decoder input), + residual (propainter.py:440-451) -----------
-  __half *sc1, *img128, *encf;
-  PP_TRY(pp_alloc(e, &sc1, (size_t)l_t * ng * 6272, "softcomp linear"));
-  PP_TRY(pp_alloc(e, &img128, (size_t)l_t * fsz, "softcomp folded"));
-  PP_TRY(pp_alloc(e, &encf, (size_t)l_t * fsz, "decoder input"));
-  PP_TRY(PPConvCall(e, "gen.sc.embedding", 1, 1, l_t * ng).in(x, 512, 0, 512).out(sc1, 6272, 0).run(st));
-  PP_TRY(pp_k_fold(sc1, 6272, img128, l_t, h4, w4, 128, gh, gw, 0, 0, st));
-  e.launches++;
-  PP_TRY(PPConvCall(e, "gen.sc.bias_conv", l_t, h4, w4).in(img128, 128, 0, 128).out(encf, 128, 0)
-             .residual(encw, 128, 0).run(st));
-
-  // ---- decoder (propainter.py:304-312) + tanh ------------------------------------------------------------
-  __half *up, *d0, *d1, *d2;
-  PP_TRY(pp_alloc(e, &up, (size_t)l_t * H * W * 64, "decoder upsampled"));
-  PP_TRY(pp_alloc(e, &d0, (size_t)l_t * h2 * w2 * 128, "decoder d0"));
-  PP_TRY(pp_alloc(e, &d1, (size_t)l_t * h2 * w2 * 64, "decoder d1"));
-  PP_TRY(pp_alloc(e, &d2, (size_t)l_t * H * W * 64, "decoder d2"));
-  PP_TRY(deconv(e, "gen.decoder.0", encf, l_t, h4, w4, 128, up, d0, 128, 128, PP_ACT_LRELU, 0.2f, st));
-  PP_TRY(PPConvCall(e, "gen.decoder.2", l_t, h2, w2).in(d0, 128, 0, 128).out(d1, 64, 0).act(PP_ACT_LRELU, 0.2f).run(st));
-  PP_TRY(deconv(e, "gen.decoder.4", d1, l_t, h2, w2, 64, up, d2, 64, 64, PP_ACT_LRELU, 0.2f, st));
-  PP_TRY(PPConvCall(e, "gen.decoder.6", l_t, H, W).in(d2, 64, 0, 64).out(pred, 4, 0).act(PP_ACT_TANH).run(st));
+  const size_t m2k = e.arena.mark();
+  __half *xl, *encl;
+  PP_TRY(pp_alloc(e, &xl, (size_t)LT * ng * 512, "local tokens"));
+  PP_TRY(pp_alloc(e, &encl, (size_t)LT * fsz, "local features"));
+  PP_TRY(pp_k_gather_blocks(xl, x, tab_dev + o_loc, LT, (long long)ng * 512 * 2, st));
+  PP_TRY(pp_k_gather_blocks(encl, encw, tab_dev + o_loc, LT, fsz * 2, st));
+  e.launches += 2;
+  // frames per chunk bounded by the workspace left (SoftComp Linear output + decoder activations)
+  const long long HWl = (long long)H * W;
+  const long long per_frame = (long long)ng * 6272 + 2 * (long long)fsz + HWl * 64 * 2 + (long long)h2 * w2 * 192;
+  long long avail = (long long)(e.arena.cap - e.arena.off) / 2 * 9 / 10;
+  int chunk = (int)(avail / per_frame);
+  if (chunk > LT) chunk = LT;
+  PP_REQUIRE(chunk >= 1, "generator: workspace too small for the decoder");
+  __half *sc1, *img128, *encf, *up, *d0, *d1, *d2;
+  PP_TRY(pp_alloc(e, &sc1, (size_t)chunk * ng * 6272, "softcomp linear"));
+  PP_TRY(pp_alloc(e, &img128, (size_t)chunk * fsz, "softcomp folded"));
+  PP_TRY(pp_alloc(e, &encf, (size_t)chunk * fsz, "decoder input"));
+  PP_TRY(pp_alloc(e, &up, (size_t)chunk * HWl * 64, "decoder upsampled"));
+  PP_TRY(pp_alloc(e, &d0, (size_t)chunk * h2 * w2 * 128, "decoder d0"));
+  PP_TRY(pp_alloc(e, &d1, (size_t)chunk * h2 * w2 * 64, "decoder d1"));
+  PP_TRY(pp_alloc(e, &d2, (size_t)chunk * HWl * 64, "decoder d2"));
+  for (int c0 = 0; c0 < LT; c0 += chunk) {
+    const int n = (c0 + chunk <= LT) ? chunk : LT - c0;
+    PP_TRY(PPConvCall(e, "gen.sc.embedding", 1, 1, n * ng).in(xl + (size_t)c0 * ng * 512, 512, 0, 512).out(sc1, 6272, 0).run(st));
+    PP_TRY(pp_k_fold(sc1, 6272, img128, n, h4, w4, 128, gh, gw, 0, 0, st));
+    e.launches++;
+    PP_TRY(PPConvCall(e, "gen.sc.bias_conv", n, h4, w4).in(img128, 128, 0, 128).out(encf, 128, 0)
+               .residual(encl + (size_t)c0 * fsz, 128, 0).run(st));
+    // decoder (propainter.py:304-312) + tanh
+    PP_TRY(deconv(e, "gen.decoder.0", encf, n, h4, w4, 128, up, d0, 128, 128, PP_ACT_LRELU, 0.2f, st));
+    PP_TRY(PPConvCall(e, "gen.decoder.2", n, h2, w2).in(d0, 128, 0, 128).out(d1, 64, 0).act(PP_ACT_LRELU, 0.2f).run(st));
+    PP_TRY(deconv(e, "gen.decoder.4", d1, n, h2, w2, 64, up, d2, 64, 64, PP_ACT_LRELU, 0.2f, st));
+    PP_TRY(PPConvCall(e, "gen.decoder.6", n, H, W).in(d2, 64, 0, 64).out(pred + (size_t)c0 * HWl * 4, 4, 0)
+               .act(PP_ACT_TANH).run(st));
+  }
+  e.arena.release(m2k);
   e.arena.release(mark0);
   return PP_OK;
+}
+
+int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __half* pred, cudaStream_t st) {
+  return pp_stage_gen_run(e, frame_ids, &t, &l_t, 1, pred, st);
 }

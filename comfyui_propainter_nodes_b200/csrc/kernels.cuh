@@ -14,6 +14,8 @@ int pp_k_upsample2x(const __half* src, int src_cs, int src_co, __half* dst, int 
 int pp_k_copy_channels(const __half* src, int src_cs, int src_co, __half* dst, int dst_cs, int dst_co, long long npix,
                        int C, cudaStream_t st);
 int pp_k_fill_f16(__half* dst, long long n, float v, cudaStream_t st);
+int pp_k_gather_blocks(void* dst, const void* src, const int* idx_dev, long long n, long long block_bytes,
+                       cudaStream_t st);
 
 // ---- RAFT (kernels_raft.cu) ---------------------------------------------------------------------
 int pp_k_instnorm_stats(const __half* x, int N, int HW, int C, float* sums /*[N][2][C]*/, cudaStream_t st);
@@ -46,8 +48,8 @@ int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half
                     const __half* offs, int offs_cs, const __half* flow, int flow_cs, int flow_co, float max_mag,
                     __half* cols, int N, int H, int W, cudaStream_t st);
 int pp_k_featprop_cond(const __half* cur, int cur_cs, const __half* prop, int prop_cs, const __half* flow_prop,
-                       const __half* flow_check, const __half* mask2, int mask_cs, __half* cond, int cond_cs, int H,
-                       int W, int C, cudaStream_t st);
+                       const __half* flow_check, const __half* mask2, int mask_cs, __half* cond, int cond_cs, int N,
+                       int H, int W, int C, cudaStream_t st);
 int pp_k_downsample_flow4(const float* flow, __half* dst, int n, int H, int W, cudaStream_t st);
 int pp_k_downsample_mask4(const float* m, __half* dst, int dst_cs, int dst_co, int n, int H, int W, cudaStream_t st);
 
@@ -56,12 +58,13 @@ int pp_k_layernorm(const __half* x, const float* gamma, const float* beta, __hal
                    int nh, int nw, cudaStream_t st);
 int pp_k_pool_tokens(const __half* x, const float* w, const float* b, __half* out, int t, int nh, int nw, int ph,
                      int pw, int C, cudaStream_t st);
-int pp_k_window_flags(const __half* mask4, int cs, int co, int lt, int h4, int w4, int gh, int gw, int nwh, int nww,
-                      int* flags, cudaStream_t st);
+int pp_k_window_flags(const __half* mask4, int cs, int co, const int* win_f0, const int* win_lt, int n_windows, int h4,
+                      int w4, int gh, int gw, int nwh, int nww, int* flags, cudaStream_t st);
 int pp_k_fold(const __half* x, int cs, __half* out, int t, int H, int W, int C, int gh, int gw, int normalise,
               int gelu, cudaStream_t st);
 int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs, const __half* pk, const __half* pv,
-                   int pool_cs, __half* out, int out_cs, const int* win_flags, const int* ring_idx, int t, int gh,
-                   int gw, int nh, int nw, int n_pool, int t_parity, cudaStream_t st);
+                   int pool_cs, __half* out, int out_cs, const int* win_flags, const int* ring_idx,
+                   const int* sw_frame_off, const int* sw_t, int n_sliding, int t_max, int gh, int gw, int nh, int nw,
+                   int n_pool, int t_parity, cudaStream_t st);
 int pp_k_composite(const __half* pred, int pred_cs, const float* masks, const uint8_t* orig, uint8_t* comp,
                    const int* frame_ids, const int* first_visit, int lt, int H, int W, cudaStream_t st);

@@ -80,6 +80,15 @@ __global__ void copy_channels(const __half* __restrict__ src, int src_cs, int sr
       *reinterpret_cast<const uint4*>(src + p * src_cs + src_co + c8 * 8);
 }
 
+// dst block j <- src block idx[j]; blocks are `block16` 16-byte units (frame-sized gathers for window batching)
+__global__ void gather_blocks(uint4* __restrict__ dst, const uint4* __restrict__ src, const int* __restrict__ idx,
+                              long long n, long long block16) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n * block16) return;
+  const long long j = i / block16, u = i - j * block16;
+  dst[i] = src[(long long)idx[j] * block16 + u];
+}
+
 __global__ void fill_f16(__half* dst, long long n, float v) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2half_rn(v);
@@ -123,6 +132,17 @@ int pp_k_copy_channels(const __half* src, int src_cs, int src_co, __half* dst, i
              "copy_channels: channels must be multiples of 8");
   if (npix == 0) return PP_OK;
   copy_channels<<<nblocks(npix * (C / 8)), TPB, 0, st>>>(src, src_cs, src_co, dst, dst_cs, dst_co, npix, C / 8);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_gather_blocks(void* dst, const void* src, const int* idx_dev, long long n, long long block_bytes,
+                       cudaStream_t st) {
+  PP_REQUIRE(block_bytes % 16 == 0, "gather_blocks: block size must be a multiple of 16 bytes");
+  if (n == 0) return PP_OK;
+  const long long b16 = block_bytes / 16;
+  gather_blocks<<<nblocks(n * b16), TPB, 0, st>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), idx_dev, n,
+                                                   b16);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

@@ -257,13 +257,23 @@ __global__ void dcn_sample(const __half* __restrict__ x0, int x0_cs, int x0_co, 
 __global__ void featprop_cond(const __half* __restrict__ cur, int cur_cs, const __half* __restrict__ prop,
                               int prop_cs, const __half2* __restrict__ flow_prop,
                               const __half2* __restrict__ flow_check, const __half* __restrict__ mask2,
-                              int mask_cs, __half* __restrict__ cond, int cond_cs, int H, int W, int C) {
+                              int mask_cs, __half* __restrict__ cond, int cond_cs, int N, int H, int W, int C) {
   const int C8 = C / 8;
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)H * W * C8) return;
+  if (idx >= (long long)N * H * W * C8) return;
   const int c8 = idx % C8;
-  const int p = idx / C8;
+  const long long pg = idx / C8;          // pixel over all N images
+  const int HWi = H * W;
+  const int img = pg / HWi;
+  const int p = pg - (long long)img * HWi;  // pixel inside the image
   const int x = p % W, y = p / W;
+  // re-base every per-image tensor
+  cur += (long long)img * HWi * cur_cs;
+  prop += (long long)img * HWi * prop_cs;
+  flow_prop += (long long)img * HWi;
+  flow_check += (long long)img * HWi;
+  mask2 += (long long)img * HWi * mask_cs;
+  cond += (long long)img * HWi * cond_cs;
   const float2 fp = __half22float2(flow_prop[p]);
   const float sx = sample_coord((float)x + fp.x, W), sy = sample_coord((float)y + fp.y, H);
   const Bilin b = bilin_setup(sx, sy, W, H);
@@ -404,12 +414,12 @@ int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half
 }
 
 int pp_k_featprop_cond(const __half* cur, int cur_cs, const __half* prop, int prop_cs, const __half* flow_prop,
-                       const __half* flow_check, const __half* mask2, int mask_cs, __half* cond, int cond_cs, int H,
-                       int W, int C, cudaStream_t st) {
+                       const __half* flow_check, const __half* mask2, int mask_cs, __half* cond, int cond_cs, int N,
+                       int H, int W, int C, cudaStream_t st) {
   PP_REQUIRE(C % 8 == 0 && cond_cs >= 2 * C + 8, "featprop_cond: bad channel counts");
-  featprop_cond<<<nblocks((long long)H * W * (C / 8)), TPB, 0, st>>>(
+  featprop_cond<<<nblocks((long long)N * H * W * (C / 8)), TPB, 0, st>>>(
       cur, cur_cs, prop, prop_cs, reinterpret_cast<const __half2*>(flow_prop),
-      reinterpret_cast<const __half2*>(flow_check), mask2, mask_cs, cond, cond_cs, H, W, C);
+      reinterpret_cast<const __half2*>(flow_check), mask2, mask_cs, cond, cond_cs, N, H, W, C);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

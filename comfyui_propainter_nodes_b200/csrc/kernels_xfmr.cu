@@ -84,11 +84,15 @@ __global__ void pool_tokens(const __half* __restrict__ x, const float* __restric
 // Window dispatch flags (propainter.py:417-428 max_pool(7,3,3) of the 1/4-res local masks, then
 // sparse_transformer.py:322-326 max over each 5x9 window and sum over local frames):
 // flag[w] = 1 if any local-frame mask pixel falls in the receptive field of any token of window w.
-// mask4: [lt][h4][w4] fp16 values at element stride cs (channel co).  One block per window.
-__global__ void window_flags(const __half* __restrict__ mask4, int cs, int co, int lt, int h4, int w4, int gh, int gw,
-                             int nww, int* __restrict__ flags) {
-  const int win = blockIdx.x;
+// mask4: [T][h4][w4] fp16 values at element stride cs (channel co); sliding window `widx` covers frames
+// win_f0[widx] .. +win_lt[widx].  One block per (5x9 token window, sliding window); flags[widx][win].
+__global__ void window_flags(const __half* __restrict__ mask4, int cs, int co, const int* __restrict__ win_f0,
+                             const int* __restrict__ win_lt, int h4, int w4, int gh, int gw, int nww,
+                             int* __restrict__ flags) {
+  const int win = blockIdx.x, widx = blockIdx.y;
   const int wy = win / nww, wx = win % nww;
+  const int lt = win_lt[widx];
+  const __half* mbase = mask4 + (long long)win_f0[widx] * h4 * w4 * cs;
   int any = 0;
   const int per_frame = 5 * 9 * 49;
   for (int i = threadIdx.x; i < lt * per_frame; i += blockDim.x) {
@@ -99,10 +103,10 @@ __global__ void window_flags(const __half* __restrict__ mask4, int cs, int co, i
     if (ty >= gh || tx >= gw) continue;  // zero padding of the mask grid
     const int y = ty * 3 - 3 + tap / 7, x = tx * 3 - 3 + tap % 7;
     if (y < 0 || y >= h4 || x < 0 || x >= w4) continue;
-    if (__half2float(mask4[(((long long)f * h4 + y) * w4 + x) * cs + co]) > 0.f) any = 1;
+    if (__half2float(mbase[(((long long)f * h4 + y) * w4 + x) * cs + co]) > 0.f) any = 1;
   }
   any = __syncthreads_or(any);
-  if (threadIdx.x == 0) flags[win] = any;
+  if (threadIdx.x == 0) flags[widx * gridDim.x + win] = any;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -204,9 +208,9 @@ int pp_k_pool_tokens(const __half* x, const float* w, const float* b, __half* ou
   return PP_OK;
 }
 
-int pp_k_window_flags(const __half* mask4, int cs, int co, int lt, int h4, int w4, int gh, int gw, int nwh, int nww,
-                      int* flags, cudaStream_t st) {
-  window_flags<<<nwh * nww, 256, 0, st>>>(mask4, cs, co, lt, h4, w4, gh, gw, nww, flags);
+int pp_k_window_flags(const __half* mask4, int cs, int co, const int* win_f0, const int* win_lt, int n_windows, int h4,
+                      int w4, int gh, int gw, int nwh, int nww, int* flags, cudaStream_t st) {
+  window_flags<<<dim3(nwh * nww, n_windows), 256, 0, st>>>(mask4, cs, co, win_f0, win_lt, h4, w4, gh, gw, nww, flags);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "pp_image_propagate": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pp_gen_begin": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "pp_gen_window": (_I, [_VP, ctypes.POINTER(_I), _I, _I, _VP, _VP]),
+    "pp_gen_run": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _VP, _VP]),
     "pp_gen_end": (_I, [_VP]),
     "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "pp_launch_count": (_LL, [_VP]),
@@ -363,6 +364,20 @@ class Engine:
         ids = (ctypes.c_int * len(frame_ids))(*[int(i) for i in frame_ids])
         pred = torch.empty(l_t, H, W, 4, device=self.device, dtype=torch.float16)
         self._check(self.lib.pp_gen_window(self.h, ids, len(frame_ids), int(l_t), _ptr(pred), self._stream()))
+        return pred
+
+    def gen_run(self, windows) -> torch.Tensor:
+        """All sliding windows in one batched pass.  windows = [(neighbor_ids, ref_ids), ...]
+        -> fp16 [sum(len(neighbor_ids)), H, W, 4] in window order."""
+        T, H, W = self._gen_shape
+        flat, wt, wl = [], [], []
+        for nb, refs in windows:
+            flat += [int(i) for i in nb] + [int(i) for i in refs]
+            wt.append(len(nb) + len(refs))
+            wl.append(len(nb))
+        arr = lambda v: (ctypes.c_int * len(v))(*v)
+        pred = torch.empty(sum(wl), H, W, 4, device=self.device, dtype=torch.float16)
+        self._check(self.lib.pp_gen_run(self.h, arr(flat), arr(wt), arr(wl), len(windows), _ptr(pred), self._stream()))
         return pred
 
     def gen_end(self):

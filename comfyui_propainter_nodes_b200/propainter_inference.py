@@ -140,14 +140,22 @@ def feature_propagation_device(inpaint_model, updated_frames, updated_masks, mas
     orig = original_frames_u8.to(dev).contiguous()
     comp = torch.zeros_like(orig)
     eng.gen_begin(updated_frames[0], md, updated_masks[0], prediction_flows[0][0], prediction_flows[1][0])
+    # every window of the schedule in one batched engine pass, then the order-dependent uint8 composite
+    preds = eng.gen_run(sched)
+    flat_ids, first = [], []
     visited = [False] * T
-    for nb, refs in sched:
-        pred = eng.gen_window(nb + refs, len(nb))
-        ids = torch.tensor(nb, dtype=torch.int32, device=dev)
-        first = torch.tensor([0 if visited[i] else 1 for i in nb], dtype=torch.int32, device=dev)
-        eng.composite(pred, md, orig, comp, ids, first)
+    for nb, _ in sched:
         for i in nb:
+            flat_ids.append(i)
+            first.append(0 if visited[i] else 1)
             visited[i] = True
+    ids_dev = torch.tensor(flat_ids, dtype=torch.int32, device=dev)
+    first_dev = torch.tensor(first, dtype=torch.int32, device=dev)
+    o = 0
+    for nb, _ in sched:   # windows in order: frames shared by consecutive windows are blended 0.5/0.5 in this order
+        n = len(nb)
+        eng.composite(preds[o:o + n], md, orig, comp, ids_dev[o:o + n], first_dev[o:o + n])
+        o += n
     eng.gen_end()
     return comp
 

@@ -67,6 +67,11 @@ PP_API int pp_gen_begin(pp_handle h, const float* updated_frames, const float* m
 /* One sliding window: frame_ids[0..l_t) are consecutive local frames, frame_ids[l_t..t) reference frames
  * (host array).  pred is fp16 [l_t][H][W][4] (rgb in [-1,1] + 1 unused lane). */
 PP_API int pp_gen_window(pp_handle h, const int* frame_ids, int t, int l_t, void* pred_f16, void* stream);
+/* All sliding windows of the clip in one batched pass: frame_ids is the concatenation of every window's
+ * [local..., reference...] ids, win_t / win_lt the per-window frame counts (host arrays).
+ * pred is fp16 [sum(win_lt)][H][W][4] in window order. */
+PP_API int pp_gen_run(pp_handle h, const int* frame_ids, const int* win_t, const int* win_lt, int n_windows,
+                      void* pred_f16, void* stream);
 PP_API int pp_gen_end(pp_handle h);
 /* uint8 composite with the reference's truncation / 0.5-0.5 blending order.  frame_ids / first_visit are
  * device int32 arrays of length l_t; orig / comp are uint8 [T][H][W][3]; masks float32 [T,1,H,W]. */
