@@ -124,6 +124,29 @@ int pp_composite(pp_handle h, const void* pred_f16, const float* masks_dilated, 
                         first_visit_dev, l_t, H, W, as_stream(stream));
 }
 
+int pp_preprocess(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
+                  int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8, float* frames, float* flow_masks,
+                  float* masks_dilated, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(image && mask && orig_u8 && frames && flow_masks && masks_dilated, "pp_preprocess: null pointer");
+  const size_t mark = e.arena.mark();
+  uint8_t* scratch;
+  PP_TRY(pp_alloc(e, &scratch, (size_t)mask_frames * H * W, "mask scratch"));
+  PP_TRY(pp_k_quantize_frames(image, orig_u8, frames, T, H, W, as_stream(stream)));
+  PP_TRY(pp_k_prepare_masks(mask, mask_frames, T, H, W, flow_mask_dilates, mask_dilates, scratch, flow_masks,
+                            masks_dilated, as_stream(stream)));
+  e.launches += 4;
+  e.arena.release(mark);
+  return PP_OK;
+}
+
+int pp_postprocess(pp_handle h, const uint8_t* comp_u8, float* image_out, long long n, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(comp_u8 && image_out, "pp_postprocess: null pointer");
+  e.launches++;
+  return pp_k_u8_to_unit_float(comp_u8, image_out, n, as_stream(stream));
+}
+
 long long pp_launch_count(pp_handle h) { return h ? reinterpret_cast<PPEngine*>(h)->launches : 0; }
 size_t pp_workspace_peak(pp_handle h) { return h ? reinterpret_cast<PPEngine*>(h)->arena.peak : 0; }
 

@@ -68,3 +68,9 @@ int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs
                    int n_pool, int t_parity, cudaStream_t st);
 int pp_k_composite(const __half* pred, int pred_cs, const float* masks, const uint8_t* orig, uint8_t* comp,
                    const int* frame_ids, const int* first_visit, int lt, int H, int W, cudaStream_t st);
+
+// ---- device pre/post-processing (kernels_pre.cu) --------------------------------------------------
+int pp_k_quantize_frames(const float* img, uint8_t* u8, float* frames, int T, int H, int W, cudaStream_t st);
+int pp_k_prepare_masks(const float* mask, int Tm, int T, int H, int W, int iters_flow, int iters_dil, uint8_t* scratch,
+                       float* flow_masks, float* masks_dilated, cudaStream_t st);
+int pp_k_u8_to_unit_float(const uint8_t* src, float* dst, long long n, cudaStream_t st);

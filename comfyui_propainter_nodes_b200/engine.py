@@ -40,6 +40,8 @@ _SIGNATURES = {
     "pp_gen_run": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _VP, _VP]),
     "pp_gen_end": (_I, [_VP]),
     "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "pp_preprocess": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "pp_postprocess": (_I, [_VP, _VP, _VP, _LL, _VP]),
     "pp_launch_count": (_LL, [_VP]),
     "pp_workspace_peak": (_SZ, [_VP]),
     "pp_profile_enable": (_I, [_VP, _I]),
@@ -388,6 +390,28 @@ class Engine:
         l_t, H, W, _ = pred.shape
         self._check(self.lib.pp_composite(self.h, _ptr(pred), _ptr(masks_dilated), _ptr(orig_u8), _ptr(comp_u8),
                                           _ptr(frame_ids_dev), _ptr(first_visit_dev), l_t, H, W, self._stream()))
+
+    def preprocess(self, image, mask, flow_mask_dilates: int, mask_dilates: int):
+        """Device version of convert_image_to_frames + prepare_frames_and_masks for the no-resize case.
+        image [T,H,W,3] float 0..1, mask [T or 1,H,W] float (host or device)
+        -> frames [1,T,3,H,W], flow_masks [1,T,1,H,W], masks_dilated [1,T,1,H,W] (float32), originals uint8 [T,H,W,3]."""
+        img = image.to(self.device, torch.float32, non_blocking=True).contiguous()
+        msk = mask.to(self.device, torch.float32, non_blocking=True).contiguous()
+        T, H, W, _ = img.shape
+        orig = torch.empty(T, H, W, 3, device=self.device, dtype=torch.uint8)
+        frames = torch.empty(T, 3, H, W, device=self.device, dtype=torch.float32)
+        fm = torch.empty(T, 1, H, W, device=self.device, dtype=torch.float32)
+        md = torch.empty_like(fm)
+        self._check(self.lib.pp_preprocess(self.h, _ptr(img), _ptr(msk), msk.shape[0], T, H, W, int(flow_mask_dilates),
+                                           int(mask_dilates), _ptr(orig), _ptr(frames), _ptr(fm), _ptr(md),
+                                           self._stream()))
+        return frames.unsqueeze(0), fm.unsqueeze(0), md.unsqueeze(0), orig
+
+    def postprocess(self, comp_u8: torch.Tensor) -> torch.Tensor:
+        """uint8 [T,H,W,3] -> float32/255 on the device (handle_output)."""
+        out = torch.empty(comp_u8.shape, device=self.device, dtype=torch.float32)
+        self._check(self.lib.pp_postprocess(self.h, _ptr(comp_u8), _ptr(out), comp_u8.numel(), self._stream()))
+        return out
 
     @property
     def launch_count(self) -> int:

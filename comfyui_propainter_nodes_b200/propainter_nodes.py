@@ -9,7 +9,9 @@ from __future__ import annotations
 
 import torch
 
-from .propainter_inference import ProPainterConfig, feature_propagation, process_inpainting
+import numpy as np
+
+from .propainter_inference import ProPainterConfig, feature_propagation_device, process_inpainting
 from .utils import image_utils as iu
 from .utils.model_utils import initialize_models
 
@@ -56,13 +58,14 @@ _TUNING_WIDGETS = (
 )
 
 
-def _run(frames_t, flow_masks_t, masks_dilated_t, originals, cfg: ProPainterConfig):
-    models = initialize_models(cfg.device, cfg.fp16)
+def _run(models, frames_t, flow_masks_t, masks_dilated_t, originals_u8, cfg: ProPainterConfig):
+    """originals_u8: uint8 [T,H,W,3] tensor (host or device)."""
     print(f"\nProcessing  {cfg.video_length} frames...")
     updated_frames, updated_masks, flows = process_inpainting(models, frames_t, flow_masks_t, masks_dilated_t, cfg)
-    composed = feature_propagation(models.inpaint_model, updated_frames, updated_masks, masks_dilated_t, flows,
-                                   originals, cfg)
-    return iu.handle_output(composed, flow_masks_t, masks_dilated_t)
+    comp = feature_propagation_device(models.inpaint_model, updated_frames, updated_masks, masks_dilated_t, flows,
+                                      originals_u8, cfg)
+    images = models.inpaint_model.engine.postprocess(comp).cpu()   # IMAGE stays a CPU tensor like the reference's
+    return images, flow_masks_t.squeeze(), masks_dilated_t.squeeze()
 
 
 class ProPainterInpaint:
@@ -84,13 +87,20 @@ class ProPainterInpaint:
                               neighbor_length, subvideo_length, raft_iter, fp16):
         check_inputs(image, mask)
         device = _compute_device()
-        frames = iu.convert_image_to_frames(image)
         n = image.size(dim=0)
-        icfg = iu.ImageConfig(width, height, mask_dilates, flow_mask_dilates, frames[0].size, n)
+        input_size = (image.size(dim=2), image.size(dim=1))       # (width, height) like PIL's Image.size
+        icfg = iu.ImageConfig(width, height, mask_dilates, flow_mask_dilates, input_size, n)
         cfg = ProPainterConfig(ref_stride, neighbor_length, subvideo_length, raft_iter, fp16, n, device,
                                icfg.process_size)
-        ft, fm, md, originals = iu.prepare_frames_and_masks(frames, mask, icfg, device)
-        return _run(ft, fm, md, originals, cfg)
+        models = initialize_models(cfg.device, cfg.fp16)
+        if tuple(icfg.process_size) == tuple(input_size):
+            # no resize: quantisation and mask dilation run on the device with the same integer semantics
+            ft, fm, md, orig = models.raft_model.engine.preprocess(image, mask, flow_mask_dilates, mask_dilates)
+        else:
+            # PIL bicubic resize on the host keeps the reference's resampling bit-identical
+            ft, fm, md, originals = iu.prepare_frames_and_masks(iu.convert_image_to_frames(image), mask, icfg, device)
+            orig = torch.from_numpy(np.stack(originals))
+        return _run(models, ft, fm, md, orig, cfg)
 
 
 class ProPainterOutpaint:
@@ -120,7 +130,8 @@ class ProPainterOutpaint:
                                icfg.outpaint_size)
         canvas, flow_masks, masks_dilated = iu.extrapolation(frames, icfg)
         ft, fm, md, originals = iu.prepare_frames_and_masks_for_outpaint(canvas, flow_masks, masks_dilated, device)
-        images, out_masks, _ = _run(ft, fm, md, originals, cfg)
+        models = initialize_models(cfg.device, cfg.fp16)
+        images, out_masks, _ = _run(models, ft, fm, md, torch.from_numpy(np.stack(originals)), cfg)
         out_w, out_h = cfg.process_size
         return images, out_masks, out_w, out_h
 

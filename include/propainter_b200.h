@@ -78,6 +78,15 @@ PP_API int pp_gen_end(pp_handle h);
 PP_API int pp_composite(pp_handle h, const void* pred_f16, const float* masks_dilated, const uint8_t* orig, uint8_t* comp,
                  const int* frame_ids_dev, const int* first_visit_dev, int l_t, int H, int W, void* stream);
 
+/* Device pre-processing when no resize is needed (reference utils/image_utils.py:106-197): image [T,H,W,3]
+ * float 0..1 -> uint8 (truncate) [T,H,W,3] + frames [T,3,H,W] in [-1,1]; mask [mask_frames,H,W] float ->
+ * 8-bit -> cross dilation x N -> flow_masks / masks_dilated [T,1,H,W] in {0,1}.  All device pointers. */
+PP_API int pp_preprocess(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
+                         int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8, float* frames, float* flow_masks,
+                         float* masks_dilated, void* stream);
+/* uint8 frames -> float32 / 255 (reference handle_output, utils/image_utils.py:276-290). */
+PP_API int pp_postprocess(pp_handle h, const uint8_t* comp_u8, float* image_out, long long n, void* stream);
+
 /* Kernels launched by this handle since creation (bench accounting), and the arena high-water mark. */
 PP_API long long pp_launch_count(pp_handle h);
 PP_API size_t pp_workspace_peak(pp_handle h);

@@ -149,3 +149,24 @@ def test_fullsize_composite_keeps_known_pixels(C):
         for i in nb:
             if cover[i] == 1:
                 assert torch.equal(parts[wi][i], full[i])
+
+
+def test_device_preprocessing_is_bit_exact(C):
+    """pp_preprocess == the host path (uint8 truncation, scipy cross dilation x N) on the same inputs."""
+    from comfyui_propainter_nodes_b200.utils import image_utils as IU
+    from comfyui_propainter_nodes_b200.synthetic import synthetic_clip
+    T, H, W = 5, 72, 104
+    img = synthetic_clip(T, H, W, 3)
+    g = torch.Generator().manual_seed(1)
+    mask = (torch.rand(T, H, W, generator=g) > 0.995).float() * torch.rand(T, H, W, generator=g)
+    mask[:, 10:20, 30:50] = 0.7
+    mask[:, 0:3, 0:3] = 1.0              # touches the border
+    eng = C.full_models().raft_model.engine
+    for fd, mdil, msk in ((8, 5, mask), (0, 3, mask), (4, 0, mask[:1])):
+        cfg = IU.ImageConfig(W, H, mdil, fd, (W, H), T)
+        ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(img), msk.clone(), cfg, torch.device("cpu"))
+        ft2, fm2, md2, orig2 = eng.preprocess(img, msk, fd, mdil)
+        assert torch.equal(ft2.cpu(), ft) and torch.equal(fm2.cpu(), fm) and torch.equal(md2.cpu(), md)
+        assert np.array_equal(orig2.cpu().numpy(), np.stack(orig))
+    u8 = torch.randint(0, 256, (2, 8, 8, 3), dtype=torch.uint8)
+    assert torch.equal(eng.postprocess(u8.to(C.DEV)).cpu(), u8.float() / 255.0)
