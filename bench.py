@@ -77,9 +77,9 @@ def synthetic_inputs():
 # CPU arm: the oracle port (the reference itself is a Python package that cannot travel to the GPU box)
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_threads():
-    """Host threads for the CPU arm: all cores up to 32 (beyond that the small 1/8-res convs of the recurrent
+    """Host threads for the CPU arm: all cores up to 16 (beyond that the small 1/8-res convs of the recurrent
     stages get slower with more threads on the 128-core host; measured in profiles/)."""
-    return min(os.cpu_count() or 1, int(os.environ.get("PP_CPU_THREADS", 32)))
+    return min(os.cpu_count() or 1, int(os.environ.get("PP_CPU_THREADS", 16)))
 
 
 def cpu_sample(n_frames=3):
@@ -151,7 +151,12 @@ def run_b200(args, rank, world):
                               PARAMS["raft_iter"], PARAMS["fp16"], T_FRAMES, dev, icfg.process_size)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
 
+    strong = args.mode == "strong" and world > 1
+
     def step():
+        if strong:
+            from comfyui_propainter_nodes_b200.parallel import inpaint_clip_distributed
+            return inpaint_clip_distributed(models, ft, fm, md, orig_dev, cfg)
         uf, um, flows = PI.process_inpainting(models, ft, fm, md, cfg)
         return PI.feature_propagation_device(models.inpaint_model, uf, um, md, flows, orig_dev, cfg)
 
@@ -197,7 +202,7 @@ def run_b200(args, rank, world):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
-    value = world * T_FRAMES / (ms_per_step / 1000.0)
+    value = (1 if strong else world) * T_FRAMES / (ms_per_step / 1000.0)
 
     # ---- end to end through the node API with host tensors (pre-processing + H2D + D2H inside)
     node = ProPainterInpaint()
@@ -221,8 +226,8 @@ def run_b200(args, rank, world):
         e2e_value = world * T_FRAMES / float(e2e_s.item())
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    h2d = ft.numel() * 4 + fm.numel() * 4 + md.numel() * 4 + orig_dev.numel()
-    d2h = orig_dev.numel()
+    h2d = img_host.numel() * 4 + mask_host.numel() * 4      # the node uploads the IMAGE / MASK float tensors
+    d2h = T_FRAMES * HEIGHT * WIDTH * 3 * 4                  # and downloads the float32 IMAGE result
 
     # ---- per-kernel timing of one extra step (CUDA events on the launch stream) for the roofline
     roof, extra, stage_ms = None, [], None
@@ -268,10 +273,11 @@ def run_b200(args, rank, world):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": T_FRAMES, "l2": "flushed between steps (256 MiB write)",
-                       "weights": "seeded synthetic checkpoints", "parallelism": f"{world} independent subvideos",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": T_FRAMES / world if strong else T_FRAMES, "l2": "flushed between steps (256 MiB write)",
+                       "weights": "seeded synthetic checkpoints", "parallelism": (f"1 subvideo sharded over {world} GPUs (RAFT pairs + windows, 2 all-gathers)" if strong
+                                       else f"{world} independent subvideos, no data-path collective"),
                        "roofline_timing": "one extra profiled step after the timed region"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "roofline_other": extra,
@@ -287,6 +293,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = one 80-frame subvideo per GPU (default); strong = ONE subvideo shared by all GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true", help="skip the node-level end-to-end leg (profiling runs)")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel timed extra step")

@@ -1,0 +1,72 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU sharding logic in comfyui_propainter_nodes_b200.parallel."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from comfyui_propainter_nodes_b200 import parallel as P
+from oracle import propainter_oracle as O
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 16, 79, 80):
+        for world in (1, 2, 3, 8):
+            parts = [P.shard_range(n, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = P.shard_sizes(n, world)
+            assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+            assert sorted(sum((P.round_robin(n, world, r) for r in range(world)), [])) == list(range(n))
+
+
+def test_composite_order_matches_reference_loop():
+    sched = O.window_schedule(80, 10, 10, 80)
+    ids, first = P.composite_order(sched)
+    assert len(ids) == 170 and sum(first) == 80
+    # frames at multiples of 5 (except the ends) are visited by 3 windows
+    assert ids.count(5) == 3 and ids.count(0) == 2 and ids.count(3) == 2
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # variable-length all-gather == concatenation in rank order
+        n = 7
+        sizes = P.shard_sizes(n, world)
+        lo, hi = P.shard_range(n, world, rank)
+        full = torch.arange(n * 6, dtype=torch.float32).view(n, 2, 3)
+        got = P.all_gather_variable(full[lo:hi].clone(), sizes)
+        assert torch.equal(got, full)
+        # an empty shard on one rank
+        sizes = [3, 0]
+        loc = full[:3].clone() if rank == 0 else full[:0].clone()
+        assert torch.equal(P.all_gather_variable(loc, sizes), full[:3])
+        # window sharding + gathered predictions reproduce the single-process composite
+        T, H, W = 12, 4, 5
+        sched = O.window_schedule(T, 4, 3, 80)
+        g = torch.Generator().manual_seed(0)
+        pred_all = torch.rand(sum(len(nb) for nb, _ in sched), H, W, 3, generator=g)   # stand-in for window outputs
+        wlo, whi = P.shard_range(len(sched), world, rank)
+        off = [0]
+        for nb, _ in sched:
+            off.append(off[-1] + len(nb))
+        mine = pred_all[off[wlo]:off[whi]].clone()
+        wsizes = [off[b] - off[a] for a, b in P.window_shards(len(sched), world)]
+        gathered = P.all_gather_variable(mine, wsizes)
+        assert torch.equal(gathered, pred_all)
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_variable_world2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 500)
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret.get(0) and ret.get(1)
