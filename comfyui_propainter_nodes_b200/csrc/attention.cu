@@ -8,8 +8,10 @@
 //   unmasked window : per frame, 45 queries x its own 45 keys
 // scale 1/sqrt(128), softmax, PV.  fp16 operands, fp32 accumulation and softmax statistics.
 //
-// Round-1 implementation: warp-level mma.sync.m16n8k16 (HMMA) with online softmax; the tcgen05/TMEM
-// version is the planned replacement.  CTA = 4 warps = 64 query rows, key tiles of 64.
+// This file: warp-level mma.sync.m16n8k16 kernel used for the UNMASKED windows (45 queries x 45 keys per frame,
+// a shape far below a tcgen05 tile); masked windows -- where the FLOPs are -- run on the tcgen05/TMEM kernel
+// in attention_tc.cu.  CTA = 4 warps = 64 query rows, key tiles of 64.
+#include "attention.cuh"
 #include "kernels.cuh"
 
 namespace {
@@ -21,17 +23,7 @@ constexpr int NT = 128;     // threads
 constexpr int WIN_TOK = 45; // 5 x 9
 constexpr int RING = 193;   // 45 own + 148 ring indices per window
 
-struct AttnParams {
-  const __half* q; const __half* k; const __half* v; int qkv_cs;  // padded token grid [t][nh*nw][cs]
-  const __half* pk; const __half* pv; int pool_cs;                // pooled tokens [t][n_pool][cs]
-  __half* out; int out_cs;                                        // unpadded grid [t][gh*gw][cs]
-  const int* win_flags;                                           // [n_sliding][n_win] 1 = masked window
-  const int* ring_idx;                                            // [n_win][193] token index in padded grid
-  const int* sw_frame_off;                                        // [n_sliding] first frame of each sliding window
-  const int* sw_t;                                                // [n_sliding] frames in each sliding window
-  int n_win, gh, gw, nh, nw, nww, n_pool, parity;
-  float scale_log2;
-};
+using AttnParams = PPAttnParams;
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {  // byte offset of a 16-byte chunk in a [rows][128] tile
   return (uint32_t)(row * 256 + ((chunk ^ (row & 7)) << 4));
@@ -66,6 +58,7 @@ __global__ void __launch_bounds__(NT) window_attention(const AttnParams p) {
   const int frame_base = p.sw_frame_off[sw];
   const int n_tind = (t - p.parity + 1) / 2;
   const bool masked = p.win_flags[sw * p.n_win + win] != 0;
+  if (masked && p.only_unmasked) return;     // masked windows run on the tcgen05 kernel (attention_tc.cu)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   int nq, nk, q_frame0;
@@ -239,8 +232,9 @@ int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs
   p.gh = gh; p.gw = gw; p.nh = nh; p.nw = nw; p.nww = nw / 9; p.n_pool = n_pool; p.parity = t_parity;
   p.n_win = (nh / 5) * (nw / 9);
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
-  const int qtiles_masked = pp_ceil_div(t_max * WIN_TOK, BQ);
-  dim3 grid(qtiles_masked > t_max ? qtiles_masked : t_max, p.n_win * 4, n_sliding);
+  p.only_unmasked = 1;
+  PP_TRY(pp_launch_attention_tc(p, n_sliding, t_max, st));   // masked windows: tcgen05 / TMEM
+  dim3 grid(t_max, p.n_win * 4, n_sliding);                  // unmasked windows: one 45x45 problem per frame
   const size_t smem = (size_t)(BQ + 4 * BKEY) * 256;
   static bool attr_set = false;
   if (!attr_set) {

@@ -1,0 +1,234 @@
+// Masked-window attention on tcgen05 tensor cores (SparseWindowAttention, sparse_transformer.py:327-357).
+//
+// One CTA (128 threads) per (128-query tile, 5x9 window, head, sliding window).  Per 128-key tile:
+//   S = Q K^T       tcgen05.mma  M=128 (queries) N=128 (keys) K=128 (d)   -> TMEM columns [0,128)
+//   softmax         thread r owns query row r (= TMEM lane r): tcgen05.ld the row, online max/sum in registers
+//                   (no shuffles), P (fp16) written to shared memory as the next A operand
+//   O += P V        tcgen05.mma  M=128 N=128 (d) K=128 (keys), V as the MN-major B operand -> TMEM [128,256)
+// O stays in TMEM for the whole key loop.  The running max is only raised when it grew by more than 8 (log2
+// units), in which case the O rows are rescaled in TMEM (tcgen05.ld/st); softmax is invariant to that shift, so
+// the result is exact while P stays within fp16 range (<= 2^8).
+// Keys are gathered by index (own 45 + ring 148 + pooled tokens of every 2nd frame) with 16-byte cp.async into
+// 128B-swizzled panels -- the window/rolled/pooled K,V tensors of the reference are never materialised.
+#include "attention.cuh"
+
+namespace {
+
+constexpr int D = 128, BQ = 128, BKEY = 128, NT = 128, WIN_TOK = 45, RING = 193;
+constexpr uint32_t PANEL = 128 * 128;          // bytes of a [128 rows][64 halves] panel
+constexpr uint32_t TILE = 2 * PANEL;           // [128][128] halves = 2 panels
+constexpr uint32_t SM_Q = 0, SM_K = TILE, SM_V = 3 * TILE, SM_P = 5 * TILE, SM_END = 6 * TILE;
+
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {  // chunk: 16-byte unit 0..15 along the 128 cols
+  return (uint32_t)(chunk >> 3) * PANEL + (uint32_t)row * 128 + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
+}
+
+__global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams p) {
+  using namespace ppx;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* mbar_s = reinterpret_cast<uint64_t*>(smem + SM_END);
+  uint64_t* mbar_o = mbar_s + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_o + 1);
+
+  const int win = blockIdx.y >> 2, head = blockIdx.y & 3, sw = blockIdx.z;
+  if (p.win_flags[sw * p.n_win + win] == 0) return;        // unmasked windows: mma.sync kernel
+  const int t = p.sw_t[sw];
+  const int frame_base = p.sw_frame_off[sw];
+  const int nq = t * WIN_TOK;
+  const int q0 = blockIdx.x * BQ;
+  if (q0 >= nq) return;
+  const int n_tind = (t - p.parity + 1) / 2;
+  const int kpf = RING + p.n_pool;
+  const int nk = n_tind * kpf;
+  const int ntiles = (nk + BKEY - 1) / BKEY;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int* ring = p.ring_idx + win * RING;
+  const long long ntok = (long long)p.nh * p.nw;
+
+  if (tid == 0) {
+    mbar_init(mbar_s, 1);
+    mbar_init(mbar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+
+  // ---- Q tile (rows beyond nq are clamped to a valid query; never stored)
+  for (int i = tid; i < BQ * 16; i += NT) {
+    const int r = i >> 4, ch = i & 15;
+    const int qi = min(q0 + r, nq - 1);
+    const int fr = frame_base + qi / WIN_TOK, pos = qi % WIN_TOK;
+    const __half* src = p.q + ((long long)fr * ntok + ring[pos]) * p.qkv_cs + head * D + ch * 8;
+    cp_async16(sbase + SM_Q + tile_off(r, ch), src, 16);
+  }
+  auto load_kv = [&](int tile, int stage) {
+    for (int i = tid; i < BKEY * 16; i += NT) {
+      const int r = i >> 4, ch = i & 15;
+      const int j = tile * BKEY + r;
+      const __half* ks = p.k; const __half* vs = p.v;
+      uint32_t nbytes = 0;
+      if (j < nk) {
+        nbytes = 16;
+        const int fi = j / kpf, w = j - fi * kpf;
+        const int fr = frame_base + p.parity + 2 * fi;
+        if (w < RING) {
+          const long long off = ((long long)fr * ntok + ring[w]) * p.qkv_cs + head * D + ch * 8;
+          ks = p.k + off; vs = p.v + off;
+        } else {
+          const long long off = ((long long)fr * p.n_pool + (w - RING)) * p.pool_cs + head * D + ch * 8;
+          ks = p.pk + off; vs = p.pv + off;
+        }
+      }
+      cp_async16(sbase + SM_K + stage * TILE + tile_off(r, ch), ks, nbytes);
+      cp_async16(sbase + SM_V + stage * TILE + tile_off(r, ch), vs, nbytes);
+    }
+    cp_async_commit();
+  };
+  load_kv(0, 0);   // one group: Q + first K/V tile
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this thread's TMEM lane (= query row)
+  const uint32_t idesc_s = umma_idesc_f16(128, 128);
+  const uint32_t idesc_o = umma_idesc_f16_bmn(128, 128);
+
+  float m_used = 0.f, m_run = -1e30f, row_sum = 0.f;
+  for (int j = 0; j < ntiles; ++j) {
+    const int stage = j & 1;
+    cp_async_wait<0>();
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {   // S = Q K^T
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t o = (uint32_t)(ks >> 2) * PANEL + (uint32_t)(ks & 3) * 32;
+        umma_f16(tmem_base, umma_desc_sw128_kmajor(sbase + SM_Q + o), umma_desc_sw128_kmajor(sbase + SM_K + stage * TILE + o),
+                 idesc_s, ks != 0 ? 1u : 0u);
+      }
+      umma_commit(mbar_s);
+    }
+    // previous P.V must be done before its K/V stage and the P buffer are overwritten
+    if (j > 0) { mbar_wait(mbar_o, (uint32_t)(j - 1) & 1u); tc_fence_after(); }
+    if (j + 1 < ntiles) load_kv(j + 1, stage ^ 1);
+    mbar_wait(mbar_s, (uint32_t)j & 1u);
+    tc_fence_after();
+
+    // ---- this thread's row of S
+    float s[128];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t raw[16];
+      tmem_ld16(lane_addr + c * 16, raw);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s[c * 16 + i] = __uint_as_float(raw[i]);
+    }
+    tmem_ld_wait();
+    const int kvalid = min(BKEY, nk - j * BKEY);
+    float m_tile = -1e30f;
+#pragma unroll
+    for (int i = 0; i < 128; ++i) {
+      s[i] = i < kvalid ? s[i] * p.scale_log2 : -1e30f;
+      m_tile = fmaxf(m_tile, s[i]);
+    }
+    const float m_new = fmaxf(m_run, m_tile);
+    int need = 0;
+    if (j == 0) m_used = m_new;
+    else need = m_new > m_used + 8.f;
+    m_run = m_new;
+    if (__syncthreads_or(need)) {
+      // rare: raise the reference max of the rows that need it and rescale their O rows in TMEM
+      const float f = need ? exp2f(m_used - m_new) : 1.f;
+      if (need) { m_used = m_new; row_sum *= f; }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t raw[16];
+        tmem_ld16(lane_addr + 128 + c * 16, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * f);
+        tmem_st16(lane_addr + 128 + c * 16, raw);
+      }
+      tmem_st_wait();
+    }
+    // ---- P = exp2(s - m_used) -> shared memory (A operand of P.V), 16 x 16-byte chunks of this row
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+      __align__(16) __half2 h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = exp2f(s[ch * 8 + 2 * e] - m_used), b = exp2f(s[ch * 8 + 2 * e + 1] - m_used);
+        row_sum += a + b;
+        h[e] = __floats2half2_rn(a, b);
+      }
+      *reinterpret_cast<uint4*>(smem + SM_P + tile_off(tid, ch)) = *reinterpret_cast<uint4*>(h);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {   // O += P V
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t adesc = umma_desc_sw128_kmajor(sbase + SM_P + (uint32_t)(ks >> 2) * PANEL + (uint32_t)(ks & 3) * 32);
+        const uint64_t bdesc = umma_desc_sw128_mnmajor(sbase + SM_V + stage * TILE + (uint32_t)ks * 2048, PANEL);
+        umma_f16(tmem_base + 128, adesc, bdesc, idesc_o, (j | ks) != 0 ? 1u : 0u);
+      }
+      umma_commit(mbar_o);
+    }
+  }
+
+  // ---- epilogue: O / row_sum -> global (unpadded grid; padding queries are dropped)
+  mbar_wait(mbar_o, (uint32_t)(ntiles - 1) & 1u);
+  tc_fence_after();
+  const int qi = q0 + tid;
+  bool store = qi < nq;
+  __half* dst = nullptr;
+  if (store) {
+    const int fr = frame_base + qi / WIN_TOK, pos = qi % WIN_TOK;
+    const int tok = ring[pos];
+    const int ty = tok / p.nw, tx = tok - ty * p.nw;
+    store = ty < p.gh && tx < p.gw;
+    dst = p.out + (((long long)fr * p.gh + ty) * p.gw + tx) * p.out_cs + head * D;
+  }
+  const float inv = 1.f / row_sum;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t raw[16];
+    tmem_ld16(lane_addr + 128 + c * 16, raw);
+    tmem_ld_wait();
+    if (store) {
+      __align__(16) __half2 h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        h[i] = __floats2half2_rn(__uint_as_float(raw[2 * i]) * inv, __uint_as_float(raw[2 * i + 1]) * inv);
+      reinterpret_cast<uint4*>(dst + c * 16)[0] = reinterpret_cast<uint4*>(h)[0];
+      reinterpret_cast<uint4*>(dst + c * 16)[1] = reinterpret_cast<uint4*>(h)[1];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace
+
+int pp_launch_attention_tc(const PPAttnParams& p, int n_sliding, int t_max, cudaStream_t st) {
+  const size_t smem = SM_END + 1024 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(pp_ceil_div(t_max * WIN_TOK, BQ), p.n_win * 4, n_sliding);
+  window_attention_tc<<<grid, NT, smem, st>>>(p);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}

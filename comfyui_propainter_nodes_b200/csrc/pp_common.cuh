@@ -145,6 +145,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 64 fp16 (128 B) with the
@@ -160,6 +169,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major B operand ([K rows][64 N-elements] panels of 128-byte rows, 128B swizzle, e.g. V[key][d] for P.V):
+// 8-row K groups are 1024 B apart (SBO), consecutive 64-element N panels are `panel_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t panel_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((panel_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 accumulate, M=128, N=n.
 __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
   uint32_t d = 0;
@@ -170,6 +191,8 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
   d |= (m >> 4) << 24;   // M / 16
   return d;
 }
+// same with the B operand MN-major (bit 16)
+__device__ __forceinline__ uint32_t umma_idesc_f16_bmn(uint32_t m, uint32_t n) { return umma_idesc_f16(m, n) | (1u << 16); }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
