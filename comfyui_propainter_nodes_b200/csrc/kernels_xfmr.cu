@@ -39,12 +39,13 @@ __global__ void layernorm512(const __half* __restrict__ x, const float* __restri
   const float var = fmaxf(q * (1.f / 512.f) - mean * mean, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
   __align__(16) __half2 o2[8];
-  const int c0 = lane * 16;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma) + lane * 4;
+  const float4* b4 = reinterpret_cast<const float4*>(beta) + lane * 4;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float a = (v[2 * i] - mean) * rstd * gamma[c0 + 2 * i] + beta[c0 + 2 * i];
-    const float b = (v[2 * i + 1] - mean) * rstd * gamma[c0 + 2 * i + 1] + beta[c0 + 2 * i + 1];
-    o2[i] = __floats2half2_rn(a, b);
+  for (int i = 0; i < 4; ++i) {
+    const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
+    o2[2 * i] = __floats2half2_rn((v[4 * i] - mean) * rstd * gg.x + bb.x, (v[4 * i + 1] - mean) * rstd * gg.y + bb.y);
+    o2[2 * i + 1] = __floats2half2_rn((v[4 * i + 2] - mean) * rstd * gg.z + bb.z, (v[4 * i + 3] - mean) * rstd * gg.w + bb.w);
   }
   long long orow = row;
   if (nh != gh || nw != gw) {
