@@ -1,9 +1,10 @@
 // Masked-window attention on tcgen05 tensor cores (SparseWindowAttention, sparse_transformer.py:327-357).
 //
-// One CTA (128 threads) per (128-query tile, 5x9 window, head, sliding window).  Per 128-key tile:
+// One CTA (256 threads) per (128-query tile, 5x9 window, head, sliding window).  Per 128-key tile:
 //   S = Q K^T       tcgen05.mma  M=128 (queries) N=128 (keys) K=128 (d)   -> TMEM columns [0,128)
-//   softmax         thread r owns query row r (= TMEM lane r): tcgen05.ld the row, online max/sum in registers
-//                   (no shuffles), P (fp16) written to shared memory as the next A operand
+//   softmax         threads r and r+128 own query row r (= TMEM lane r), 64 key columns each: tcgen05.ld, online
+//                   max/sum in registers (one shared-memory exchange of the row max per tile, no shuffles),
+//                   P (fp16) written to shared memory as the next A operand
 //   O += P V        tcgen05.mma  M=128 N=128 (d) K=128 (keys), V as the MN-major B operand -> TMEM [128,256)
 // O stays in TMEM for the whole key loop.  The running max is only raised when it grew by more than 8 (log2
 // units), in which case the O rows are rescaled in TMEM (tcgen05.ld/st); softmax is invariant to that shift, so
@@ -14,7 +15,7 @@
 
 namespace {
 
-constexpr int D = 128, BQ = 128, BKEY = 128, NT = 128, WIN_TOK = 45, RING = 193;
+constexpr int D = 128, BQ = 128, BKEY = 128, NT = 256, WIN_TOK = 45, RING = 193;
 constexpr uint32_t PANEL = 128 * 128;          // bytes of a [128 rows][64 halves] panel
 constexpr uint32_t TILE = 2 * PANEL;           // [128][128] halves = 2 panels
 constexpr uint32_t SM_Q = 0, SM_K = TILE, SM_V = 3 * TILE, SM_P = 5 * TILE, SM_END = 6 * TILE;
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
   uint64_t* mbar_s = reinterpret_cast<uint64_t*>(smem + SM_END);
   uint64_t* mbar_o = mbar_s + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_o + 1);
+  float* xch = reinterpret_cast<float*>(smem + SM_END + 64);   // [2][128] row-max / row-sum exchange
 
   const int win = blockIdx.y >> 2, head = blockIdx.y & 3, sw = blockIdx.z;
   if (p.win_flags[sw * p.n_win + win] == 0) return;        // unmasked windows: mma.sync kernel
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this thread's TMEM lane (= query row)
+  const int row = tid & 127, half = tid >> 7;                             // query row, which 64 key/d columns
+  const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // this thread's TMEM lane (= query row)
   const uint32_t idesc_s = umma_idesc_f16(128, 128);
   const uint32_t idesc_o = umma_idesc_f16_bmn(128, 128);
 
@@ -121,23 +124,29 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
     mbar_wait(mbar_s, (uint32_t)j & 1u);
     tc_fence_after();
 
-    // ---- this thread's row of S
-    float s[128];
+    // ---- this thread's 64 columns of its S row
+    float s[64];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       uint32_t raw[16];
-      tmem_ld16(lane_addr + c * 16, raw);
+      tmem_ld16(lane_addr + half * 64 + c * 16, raw);
 #pragma unroll
       for (int i = 0; i < 16; ++i) s[c * 16 + i] = __uint_as_float(raw[i]);
     }
     tmem_ld_wait();
-    const int kvalid = min(BKEY, nk - j * BKEY);
-    float m_tile = -1e30f;
+    const int kvalid = min(BKEY, nk - j * BKEY) - half * 64;   // valid columns among this thread's 64
+    if (kvalid < 64) {
 #pragma unroll
-    for (int i = 0; i < 128; ++i) {
-      s[i] = i < kvalid ? s[i] * p.scale_log2 : -1e30f;
-      m_tile = fmaxf(m_tile, s[i]);
+      for (int i = 0; i < 64; ++i) if (i >= kvalid) s[i] = -1e30f;
     }
+    float mx[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+      mx[0] = fmaxf(mx[0], s[i]); mx[1] = fmaxf(mx[1], s[i + 1]); mx[2] = fmaxf(mx[2], s[i + 2]); mx[3] = fmaxf(mx[3], s[i + 3]);
+    }
+    xch[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
+    __syncthreads();
+    const float m_tile = fmaxf(xch[row], xch[128 + row]);
     const float m_new = fmaxf(m_run, m_tile);
     int need = 0;
     if (j == 0) m_used = m_new;
@@ -148,28 +157,31 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
       const float f = need ? exp2f(m_used - m_new) : 1.f;
       if (need) { m_used = m_new; row_sum *= f; }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t raw[16];
-        tmem_ld16(lane_addr + 128 + c * 16, raw);
+        tmem_ld16(lane_addr + 128 + half * 64 + c * 16, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * f);
-        tmem_st16(lane_addr + 128 + c * 16, raw);
+        tmem_st16(lane_addr + 128 + half * 64 + c * 16, raw);
       }
       tmem_st_wait();
     }
-    // ---- P = exp2(s - m_used) -> shared memory (A operand of P.V), 16 x 16-byte chunks of this row
+    // ---- P = exp2(s*scale - m_used) -> shared memory (A operand of P.V): this thread's 8 x 16-byte chunks
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
+    for (int ch = 0; ch < 8; ++ch) {
       __align__(16) __half2 h[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float a = exp2f(s[ch * 8 + 2 * e] - m_used), b = exp2f(s[ch * 8 + 2 * e + 1] - m_used);
-        row_sum += a + b;
+        const float a = exp2f(fmaf(s[ch * 8 + 2 * e], p.scale_log2, -m_used));
+        const float b = exp2f(fmaf(s[ch * 8 + 2 * e + 1], p.scale_log2, -m_used));
+        ps[e] += a + b;
         h[e] = __floats2half2_rn(a, b);
       }
-      *reinterpret_cast<uint4*>(smem + SM_P + tile_off(tid, ch)) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(smem + SM_P + tile_off(row, half * 8 + ch)) = *reinterpret_cast<uint4*>(h);
     }
+    row_sum += (ps[0] + ps[1]) + (ps[2] + ps[3]);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -188,7 +200,10 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
   // ---- epilogue: O / row_sum -> global (unpadded grid; padding queries are dropped)
   mbar_wait(mbar_o, (uint32_t)(ntiles - 1) & 1u);
   tc_fence_after();
-  const int qi = q0 + tid;
+  xch[half * 128 + row] = row_sum;
+  __syncthreads();
+  const float inv = 1.f / (xch[row] + xch[128 + row]);
+  const int qi = q0 + row;
   bool store = qi < nq;
   __half* dst = nullptr;
   if (store) {
@@ -196,13 +211,12 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
     const int tok = ring[pos];
     const int ty = tok / p.nw, tx = tok - ty * p.nw;
     store = ty < p.gh && tx < p.gw;
-    dst = p.out + (((long long)fr * p.gh + ty) * p.gw + tx) * p.out_cs + head * D;
+    dst = p.out + (((long long)fr * p.gh + ty) * p.gw + tx) * p.out_cs + head * D + half * 64;
   }
-  const float inv = 1.f / row_sum;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint32_t raw[16];
-    tmem_ld16(lane_addr + 128 + c * 16, raw);
+    tmem_ld16(lane_addr + 128 + half * 64 + c * 16, raw);
     tmem_ld_wait();
     if (store) {
       __align__(16) __half2 h[8];
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
 }  // namespace
 
 int pp_launch_attention_tc(const PPAttnParams& p, int n_sliding, int t_max, cudaStream_t st) {
-  const size_t smem = SM_END + 1024 + 64;
+  const size_t smem = SM_END + 1024 + 64 + 2 * 128 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     PP_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -117,6 +117,11 @@ struct PPConvCall {
 
 void pp_build_ring_indices(int nh, int nw, std::vector<int>& out);
 
+// 3x3 conv with <= 3 output channels through the direct kernel; weights registered as tensors
+// "<name>.w" (fp16 [cout][9][C]) and "<name>.b" (fp32 [cout]).
+int pp_small_conv(PPEngine& e, const std::string& name, const __half* x, int x_cs, int x_co, int C, int cout, void* out,
+                  int out_cs, int out_co, int out_fp32, int act_tanh, int N, int H, int W, cudaStream_t st);
+
 // ---- stages ---------------------------------------------------------------------------------------
 int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int iters, float* flows_f, float* flows_b,
                   cudaStream_t st);

@@ -74,3 +74,8 @@ int pp_k_quantize_frames(const float* img, uint8_t* u8, float* frames, int T, in
 int pp_k_prepare_masks(const float* mask, int Tm, int T, int H, int W, int iters_flow, int iters_dil, uint8_t* scratch,
                        float* flow_masks, float* masks_dilated, cudaStream_t st);
 int pp_k_u8_to_unit_float(const uint8_t* src, float* dst, long long n, cudaStream_t st);
+
+// ---- direct 3x3 conv for <= 3 output channels (conv_small.cu) ---------------------------------------
+int pp_k_conv3x3_small(const __half* x, int x_cs, int x_co, const __half* w, const float* bias, int cout, void* out,
+                       int out_cs, int out_co, int out_fp32, int act_tanh, int N, int H, int W, int C,
+                       cudaStream_t st);

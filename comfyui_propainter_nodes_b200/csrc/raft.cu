@@ -232,7 +232,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
         // FlowHead (update.py:6-14)
         PP_TRY(PPConvCall(e, "raft.update.fh1", B, h8, w8).in(hx, 384, 0, 128).out(fh, 256, 0)
                    .act(PP_ACT_RELU).run(st));
-        PP_TRY(PPConvCall(e, "raft.update.fh2", B, h8, w8).in(fh, 256, 0, 256).out(delta, 2, 0, 1).run(st));
+        PP_TRY(pp_small_conv(e, "raft.update.fh2", fh, 256, 0, 256, 2, delta, 2, 0, 1, 0, B, h8, w8, st));
         PP_TRY(pp_k_raft_coords_update(delta, coords1, flow8, hx, 384, 382, B, h8, w8, st));
         e.launches++;
       }

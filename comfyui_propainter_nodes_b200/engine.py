@@ -315,9 +315,22 @@ class Engine:
         self._keep.append(t)
         self._check(self.lib.pp_register_tensor(self.h, name.encode(), _ptr(t), t.numel() * 4))
 
+    # layers with <= 3 output channels run on the direct 3x3 kernel (csrc/conv_small.cu), not the implicit GEMM
+    SMALL_CONVS = ("raft.update.fh2", "gen.decoder.6", "rfc.upsample.deconv")
+
+    def register_small_conv(self, name, w, b):
+        """[cout, C, 3, 3] -> fp16 [cout][9][C] (tap-major) + fp32 bias, as tensors '<name>.w' / '<name>.b'."""
+        wt = w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1]).contiguous().half().to(self.device)
+        self._keep.append(wt)
+        self._check(self.lib.pp_register_tensor(self.h, (name + ".w").encode(), _ptr(wt), wt.numel() * 2))
+        self.register_tensor(name + ".b", b)
+
     def load_weights(self, raft_sd, rfc_sd, gen_sd):
         convs, tens = build_layers(raft_sd, rfc_sd, gen_sd)
         for name, (w, b, groups, cin_map) in convs.items():
+            if name in self.SMALL_CONVS:
+                self.register_small_conv(name, w, b)
+                continue
             self.register_conv(name, w, b, groups, cin_map)
         for name, t in tens.items():
             self.register_tensor(name, t)
