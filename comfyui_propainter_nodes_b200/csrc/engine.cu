@@ -97,14 +97,15 @@ int PPConvCall::run(cudaStream_t st) {
   return pp_launch_conv(p, st);
 }
 
-int pp_small_conv(PPEngine& e, const std::string& name, const __half* x, int x_cs, int x_co, int C, int cout, void* out,
-                  int out_cs, int out_co, int out_fp32, int act_tanh, int N, int H, int W, cudaStream_t st) {
-  const void *w, *b;
-  PP_TRY(pp_get_tensor(e, name + ".w", &w));
+int pp_small_conv(PPEngine& e, const std::string& name, const __half* x, int x_cs, int x_co, int C, int cout, void* z,
+                  int z_fp32, void* out, int out_cs, int out_co, int out_fp32, int act_tanh, int N, int H, int W,
+                  cudaStream_t st) {
+  const void* b;
   PP_TRY(pp_get_tensor(e, name + ".b", &b));
+  PP_TRY(PPConvCall(e, name + ".taps", N, H, W).in(x, x_cs, x_co, C).geom(1, 1, 0, 0).out(z, 32, 0, z_fp32).run(st));
   e.launches++;
   const double rows = (double)N * H * W;
-  PPProfScope ps(e, "small:" + name, rows, 2.0 * rows * cout * 9 * C, rows * (C * 2 + cout * (out_fp32 ? 4 : 2)), st);
-  return pp_k_conv3x3_small(x, x_cs, x_co, static_cast<const __half*>(w), static_cast<const float*>(b), cout, out, out_cs,
-                            out_co, out_fp32, act_tanh, N, H, W, C, st);
+  PPProfScope ps(e, "tap_sum:" + name, rows, 0.0, rows * (9 * cout * (z_fp32 ? 4 : 2) + cout * (out_fp32 ? 4 : 2)), st);
+  return pp_k_tap_sum3x3(z, z_fp32, 32, static_cast<const float*>(b), cout, out, out_cs, out_co, out_fp32, act_tanh, N, H, W,
+                         st);
 }

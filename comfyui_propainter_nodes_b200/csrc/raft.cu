@@ -139,7 +139,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
   size_t corr_elems = 0;
   for (int l = 0; l < 4; ++l) corr_elems += (size_t)P * lvl_h[l] * lvl_w[l];
   const size_t per_pair = corr_elems * 2 + (size_t)P * (384 + 128 + 128 + 328 + 256 + 256 + 128 + 8 + 256) * 2 +
-                          (size_t)P * 4 * 4 + (size_t)P * 576 * 2;
+                          (size_t)P * 4 * 4 + (size_t)P * 32 * 4 + (size_t)P * 576 * 2;
   const size_t avail = e.arena.cap - e.arena.off;
   int max_pairs = (int)(avail * 9 / 10 / per_pair);
   PP_REQUIRE(max_pairs >= 1, "raft: workspace too small for one frame pair (%zu bytes needed)", per_pair);
@@ -199,6 +199,8 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
       PP_TRY(pp_alloc(e, &fh, (size_t)M * 256, "flow head"));
       PP_TRY(pp_alloc(e, &coords1, (size_t)M * 2, "coords1"));
       PP_TRY(pp_alloc(e, &delta, (size_t)M * 2, "delta"));
+      float* ztap;
+      PP_TRY(pp_alloc(e, &ztap, (size_t)M * 32, "flow head tap products"));
       PP_TRY(pp_k_cnet_split(cmap + (size_t)f1 * P * 256, hx, 384, M, st));
       PP_TRY(pp_k_raft_coords_init(coords1, flow8, hx, 384, 382, B, h8, w8, st));
       e.launches += 2;
@@ -232,7 +234,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
         // FlowHead (update.py:6-14)
         PP_TRY(PPConvCall(e, "raft.update.fh1", B, h8, w8).in(hx, 384, 0, 128).out(fh, 256, 0)
                    .act(PP_ACT_RELU).run(st));
-        PP_TRY(pp_small_conv(e, "raft.update.fh2", fh, 256, 0, 256, 2, delta, 2, 0, 1, 0, B, h8, w8, st));
+        PP_TRY(pp_small_conv(e, "raft.update.fh2", fh, 256, 0, 256, 2, ztap, 1, delta, 2, 0, 1, 0, B, h8, w8, st));
         PP_TRY(pp_k_raft_coords_update(delta, coords1, flow8, hx, 384, 382, B, h8, w8, st));
         e.launches++;
       }

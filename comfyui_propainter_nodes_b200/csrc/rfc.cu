@@ -147,7 +147,10 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
              .act(PP_ACT_LRELU, 0.2f).run(st));
   PP_TRY(PPConvCall(e, "rfc.upsample.0", N, h2, w2).in(d1, 32, 0, 32).out(u0, 32, 0).act(PP_ACT_LRELU, 0.2f).run(st));
   PP_TRY(pp_k_upsample2x(u0, 32, 0, up, 32, 0, N, h2, w2, 32, st));
-  PP_TRY(pp_small_conv(e, "rfc.upsample.deconv", up, 32, 0, 32, 2, pred, 2, 0, 0, 0, N, H, W, st));
+  // 32->2 tail: per-tap partial products (fp32 scratch) + tap gather
+  float* ztap;
+  PP_TRY(pp_alloc(e, &ztap, (size_t)N * HW * 32, "rfc tap products"));
+  PP_TRY(pp_small_conv(e, "rfc.upsample.deconv", up, 32, 0, 32, 2, ztap, 1, pred, 2, 0, 0, 0, N, H, W, st));
   e.launches += 3;
 
   // ---- combine_flow (:389-400) and un-flip ----------------------------------------------------------

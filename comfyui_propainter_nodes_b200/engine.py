@@ -315,14 +315,14 @@ class Engine:
         self._keep.append(t)
         self._check(self.lib.pp_register_tensor(self.h, name.encode(), _ptr(t), t.numel() * 4))
 
-    # layers with <= 3 output channels run on the direct 3x3 kernel (csrc/conv_small.cu), not the implicit GEMM
+    # 3x3 layers with <= 3 output channels: 1x1 GEMM producing the 9*cout per-tap partial products + tap gather
     SMALL_CONVS = ("raft.update.fh2", "gen.decoder.6", "rfc.upsample.deconv")
 
     def register_small_conv(self, name, w, b):
-        """[cout, C, 3, 3] -> fp16 [cout][9][C] (tap-major) + fp32 bias, as tensors '<name>.w' / '<name>.b'."""
-        wt = w.detach().float().permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1]).contiguous().half().to(self.device)
-        self._keep.append(wt)
-        self._check(self.lib.pp_register_tensor(self.h, (name + ".w").encode(), _ptr(wt), wt.numel() * 2))
+        """[cout, C, 3, 3] -> 1x1 conv '<name>.taps' with output channel tap*cout + c, bias tensor '<name>.b'."""
+        cout, C = w.shape[0], w.shape[1]
+        wt = w.detach().float().permute(2, 3, 0, 1).reshape(9 * cout, C, 1, 1)   # [(ky,kx,c), ch]
+        self.register_conv(name + ".taps", wt, None)
         self.register_tensor(name + ".b", b)
 
     def load_weights(self, raft_sd, rfc_sd, gen_sd):

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 def synthetic_clip(T: int, H: int, W: int, seed: int = 1234) -> torch.Tensor:
     """IMAGE tensor [T,H,W,3] float32 in [0,1] (ComfyUI layout)."""
     g = torch.Generator().manual_seed(seed)
-    pad = 160  # room for the translation
+    pad = max(160, int(1.5 * T) + 8)  # room for the translation (160 keeps the <=100-frame clips unchanged)
     base = torch.rand(1, 3, (H + pad) // 8 + 2, (W + pad) // 8 + 2, generator=g)
     big = F.interpolate(base, scale_factor=8, mode="bicubic", align_corners=False).clamp(0, 1)[0]
     frames = []
