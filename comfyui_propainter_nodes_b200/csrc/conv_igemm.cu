@@ -8,6 +8,8 @@
 //               cp.async.bulk (TMA engine) per stage
 // Pipelines: `stages` smem slots (full/empty mbarriers) that keep filling across tile boundaries, and two
 // TMEM accumulators (acc_full/acc_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <string.h>
+
 #include "conv_igemm.cuh"
 
 namespace {
@@ -124,6 +126,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
+  // previous kernel in the stream; from here on we read its outputs.  Let our own dependents start their prologue.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 4) {
     // ------------------------------------------------------------------ epilogue warps (TMEM lanes 32*warp..)
@@ -394,7 +400,18 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
   const long long total_tiles = (long long)pp_ceil_div(p.M_total, BM) * (p.Cout_g_pad / p.BN) * p.groups;
   PP_REQUIRE(total_tiles < (1LL << 31), "conv: too many tiles");
   const int grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
-  conv_igemm_kernel<<<grid, NUM_THREADS, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: see griddepcontrol.wait in the kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_igemm_kernel, p));
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

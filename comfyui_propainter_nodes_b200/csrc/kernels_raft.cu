@@ -112,49 +112,81 @@ struct CorrLevels {
 };
 
 // One warp per query pixel.  For a given (pixel, level) all 81 outputs share the same bilinear fractions
-// (the window offsets are integers), so the warp stages the 10x10 tap window of each level in shared memory
-// once (400 taps, zero outside the map) and every lane then blends 4 staged taps per output:
+// (the window offsets are integers), so the warp stages the tap window of each level in shared memory once
+// (zero outside the map) and every lane then blends 4 staged taps per output:
 //   out[l*81 + i*9 + j] = bilerp(T_l[j..j+1][i..i+1])      (i moves x, j moves y -- the meshgrid quirk)
-// Global traffic per pixel = the algorithmic 8 B coords + 400 taps + 324 outputs; stores are contiguous.
+// Taps are fetched as aligned fp16 pairs (12 columns starting at the even column <= x0-4; map widths are even at
+// every level for the sizes ProPainter produces, odd widths take the scalar path), which halves the load
+// instructions; output channel -> (level, tap offset) comes from a small table built once per block.
+// Global traffic per pixel = the algorithmic 8 B coords + 4x100 taps + 324 outputs; stores are contiguous.
 constexpr int LOOKUP_WARPS = 8;
+constexpr int TAP_COLS = 12;   // staged columns per tap row
+constexpr int TAP_STRIDE = 10 * TAP_COLS;
 
 __global__ void __launch_bounds__(LOOKUP_WARPS * 32) corr_lookup(CorrLevels lv, const float* __restrict__ coords,
                                                                  __half* __restrict__ out, int out_cs, long long nq,
                                                                  int h8, int w8) {
-  __shared__ float taps[LOOKUP_WARPS][4][104];
+  __shared__ float taps[LOOKUP_WARPS][4][TAP_STRIDE];
+  __shared__ float frac[LOOKUP_WARPS][4][2];
+  __shared__ int phase[LOOKUP_WARPS][4];
+  __shared__ unsigned short otab[352];
+  for (int c = threadIdx.x; c < 352; c += blockDim.x) {
+    unsigned short e = 0xFFFF;
+    if (c < 324) {
+      const int l = c / 81, r = c - l * 81, i = r / 9, j = r - i * 9;
+      e = (unsigned short)((l << 12) | (j * TAP_COLS + i));
+    }
+    otab[c] = e;
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = (long long)blockIdx.x * LOOKUP_WARPS + warp;
   if (q >= nq) return;
   const float cx = coords[q * 2], cy = coords[q * 2 + 1];
-  float ax[4], ay[4];
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const float inv = 1.f / (float)(1 << l);
     const int h = h8 >> l, w = w8 >> l;
     const float x = cx * inv, y = cy * inv;
     const float fx = floorf(x), fy = floorf(y);
-    ax[l] = x - fx; ay[l] = y - fy;
     const int x0 = (int)fx - 4, y0 = (int)fy - 4;
+    const int xa = x0 & ~1;                       // even column <= x0 (also for negative x0)
+    if (lane == 0) { frac[warp][l][0] = x - fx; frac[warp][l][1] = y - fy; phase[warp][l] = x0 - xa; }
     const __half* m = lv.p[l] + q * (long long)(h * w);
-    for (int t = lane; t < 100; t += 32) {
-      const int ty = t / 10, tx = t - ty * 10;
-      const int yy = y0 + ty, xx = x0 + tx;
-      float v = 0.f;
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = __half2float(m[yy * w + xx]);
-      taps[warp][l][t] = v;
+    float* T = taps[warp][l];
+    if ((w & 1) == 0) {
+#pragma unroll
+      for (int t2 = lane; t2 < 60; t2 += 32) {    // 10 rows x 6 aligned pairs
+        const int ty = t2 / 6, tp = t2 - ty * 6;
+        const int yy = y0 + ty, xx = xa + 2 * tp;
+        float2 v = make_float2(0.f, 0.f);
+        if ((unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w)
+          v = __half22float2(*reinterpret_cast<const __half2*>(m + yy * w + xx));
+        T[ty * TAP_COLS + 2 * tp] = v.x;
+        T[ty * TAP_COLS + 2 * tp + 1] = v.y;
+      }
+    } else {
+      for (int t = lane; t < TAP_STRIDE; t += 32) {
+        const int ty = t / TAP_COLS, tx = t - ty * TAP_COLS;
+        const int yy = y0 + ty, xx = xa + tx;
+        float v = 0.f;
+        if ((unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w) v = __half2float(m[yy * w + xx]);
+        T[t] = v;
+      }
     }
   }
   __syncwarp();
   __half* o = out + q * out_cs;
   for (int c = lane; c < out_cs; c += 32) {
+    const unsigned e = otab[c];
     float val = 0.f;
-    if (c < 324) {
-      const int l = c / 81, r = c - l * 81;
-      const int i = r / 9, j = r - i * 9;
-      const float* T = taps[warp][l];
-      const float a = ax[l], b = ay[l];
-      val = (1.f - b) * ((1.f - a) * T[j * 10 + i] + a * T[j * 10 + i + 1]) +
-            b * ((1.f - a) * T[(j + 1) * 10 + i] + a * T[(j + 1) * 10 + i + 1]);
+    if (e != 0xFFFF) {
+      const int l = e >> 12;
+      const float* T = taps[warp][l] + (e & 0xFFF) + phase[warp][l];
+      const float a = frac[warp][l][0], b = frac[warp][l][1];
+      const float top = T[0] + a * (T[1] - T[0]);
+      const float bot = T[TAP_COLS] + a * (T[TAP_COLS + 1] - T[TAP_COLS]);
+      val = top + b * (bot - top);
     }
     o[c] = __float2half_rn(val);
   }
@@ -265,7 +297,7 @@ int pp_k_corr_pool(const __half* src, __half* dst, long long nq, int h, int w, c
 
 int pp_k_corr_lookup(const __half* l0, const __half* l1, const __half* l2, const __half* l3, const float* coords,
                      __half* out, int out_cs, long long nq, int P, int h8, int w8, cudaStream_t st) {
-  PP_REQUIRE(out_cs >= 324, "corr_lookup: out_cs=%d < 324", out_cs);
+  PP_REQUIRE(out_cs >= 324 && out_cs <= 352, "corr_lookup: out_cs=%d not in [324,352]", out_cs);
   CorrLevels lv;
   lv.p[0] = l0; lv.p[1] = l1; lv.p[2] = l2; lv.p[3] = l3;
   (void)P;
