@@ -1,11 +1,11 @@
 // Masked-window attention on tcgen05 tensor cores (SparseWindowAttention, sparse_transformer.py:327-357).
 //
-// One CTA (256 threads) per (128-query tile, 5x9 window, head, sliding window).  Per 128-key tile:
-//   S = Q K^T       tcgen05.mma  M=128 (queries) N=128 (keys) K=128 (d)   -> TMEM columns [0,128)
-//   softmax         threads r and r+128 own query row r (= TMEM lane r), 64 key columns each: tcgen05.ld, online
+// One CTA (256 threads, two per SM) per (128-query tile, 5x9 window, head, sliding window).  Per 64-key tile:
+//   S = Q K^T       tcgen05.mma  M=128 (queries) N=64 (keys) K=128 (d)    -> TMEM columns [0,64)
+//   softmax         threads r and r+128 own query row r (= TMEM lane r), 32 key columns each: tcgen05.ld, online
 //                   max/sum in registers (one shared-memory exchange of the row max per tile, no shuffles),
 //                   P (fp16) written to shared memory as the next A operand
-//   O += P V        tcgen05.mma  M=128 N=128 (d) K=128 (keys), V as the MN-major B operand -> TMEM [128,256)
+//   O += P V        tcgen05.mma  M=128 N=128 (d) K=64 (keys), V as the MN-major B operand  -> TMEM [128,256)
 // O stays in TMEM for the whole key loop.  The running max is only raised when it grew by more than 8 (log2
 // units), in which case the O rows are rescaled in TMEM (tcgen05.ld/st); softmax is invariant to that shift, so
 // the result is exact while P stays within fp16 range (<= 2^8).
@@ -15,25 +15,32 @@
 
 namespace {
 
-constexpr int D = 128, BQ = 128, BKEY = 128, NT = 256, WIN_TOK = 45, RING = 193;
-constexpr uint32_t PANEL = 128 * 128;          // bytes of a [128 rows][64 halves] panel
-constexpr uint32_t TILE = 2 * PANEL;           // [128][128] halves = 2 panels
-constexpr uint32_t SM_Q = 0, SM_K = TILE, SM_V = 3 * TILE, SM_P = 5 * TILE, SM_END = 6 * TILE;
+constexpr int D = 128, BQ = 128, BKEY = 64, NT = 256, WIN_TOK = 45, RING = 193;
+constexpr int CPT = BKEY / 2;
+constexpr int TMEM_COLS = 256;                 // S: BKEY columns at 0, O: 128 columns at O_COL
+constexpr int O_COL = 128;                   // key columns per thread (two threads per query row)
+constexpr uint32_t QPANEL = BQ * 128;           // bytes of a [128 rows][64 halves] panel (Q, P)
+constexpr uint32_t KPANEL = BKEY * 128;         // bytes of a [BKEY rows][64 halves] panel (K, V)
+constexpr uint32_t QTILE = 2 * QPANEL;          // Q: [128][128 d]
+constexpr uint32_t KTILE = 2 * KPANEL;          // K or V: [BKEY][128 d]
+constexpr uint32_t PTILE = (BKEY / 64) * QPANEL;  // P: [128][BKEY keys]
+// 112 KiB per CTA so that two CTAs share an SM: one CTA's softmax overlaps the other's MMAs and gathers
+constexpr uint32_t SM_Q = 0, SM_K = QTILE, SM_V = SM_K + 2 * KTILE, SM_P = SM_V + 2 * KTILE, SM_END = SM_P + PTILE;
 
-__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {  // chunk: 16-byte unit 0..15 along the 128 cols
-  return (uint32_t)(chunk >> 3) * PANEL + (uint32_t)row * 128 + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
+// byte offset of 16-byte chunk `chunk` (along the 64-wide panels) of row `row` in a tile whose panels are `panel` bytes
+__device__ __forceinline__ uint32_t tile_off(uint32_t panel, int row, int chunk) {
+  return (uint32_t)(chunk >> 3) * panel + (uint32_t)row * 128 + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
 }
 
-__global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams p) {
+__global__ void __launch_bounds__(NT, 2) window_attention_tc(const PPAttnParams p) {
   using namespace ppx;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   const uint32_t sbase = smem_u32(smem);
   uint64_t* mbar_s = reinterpret_cast<uint64_t*>(smem + SM_END);
   uint64_t* mbar_o = mbar_s + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_o + 1);
-  float* xch = reinterpret_cast<float*>(smem + SM_END + 64);   // [2][128] row-max / row-sum exchange
+  __half* xmax = reinterpret_cast<__half*>(smem + SM_END + 64);   // [2][128] per-tile row-max exchange
+  float* xsum = reinterpret_cast<float*>(smem + SM_Q);            // [2][128] row-sum exchange (Q tile is dead by then)
 
   const int win = blockIdx.y >> 2, head = blockIdx.y & 3, sw = blockIdx.z;
   if (p.win_flags[sw * p.n_win + win] == 0) return;        // unmasked windows: mma.sync kernel
@@ -56,7 +63,7 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
     mbar_fence_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
 
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
     const int qi = min(q0 + r, nq - 1);
     const int fr = frame_base + qi / WIN_TOK, pos = qi % WIN_TOK;
     const __half* src = p.q + ((long long)fr * ntok + ring[pos]) * p.qkv_cs + head * D + ch * 8;
-    cp_async16(sbase + SM_Q + tile_off(r, ch), src, 16);
+    cp_async16(sbase + SM_Q + tile_off(QPANEL, r, ch), src, 16);
   }
   auto load_kv = [&](int tile, int stage) {
     for (int i = tid; i < BKEY * 16; i += NT) {
@@ -86,8 +93,8 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
           ks = p.pk + off; vs = p.pv + off;
         }
       }
-      cp_async16(sbase + SM_K + stage * TILE + tile_off(r, ch), ks, nbytes);
-      cp_async16(sbase + SM_V + stage * TILE + tile_off(r, ch), vs, nbytes);
+      cp_async16(sbase + SM_K + stage * KTILE + tile_off(KPANEL, r, ch), ks, nbytes);
+      cp_async16(sbase + SM_V + stage * KTILE + tile_off(KPANEL, r, ch), vs, nbytes);
     }
     cp_async_commit();
   };
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
   const uint32_t tmem_base = *tmem_slot;
   const int row = tid & 127, half = tid >> 7;                             // query row, which 64 key/d columns
   const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // this thread's TMEM lane (= query row)
-  const uint32_t idesc_s = umma_idesc_f16(128, 128);
+  const uint32_t idesc_s = umma_idesc_f16(128, BKEY);
   const uint32_t idesc_o = umma_idesc_f16_bmn(128, 128);
 
   float m_used = 0.f, m_run = -1e30f, row_sum = 0.f;
@@ -112,9 +119,10 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t o = (uint32_t)(ks >> 2) * PANEL + (uint32_t)(ks & 3) * 32;
-        umma_f16(tmem_base, umma_desc_sw128_kmajor(sbase + SM_Q + o), umma_desc_sw128_kmajor(sbase + SM_K + stage * TILE + o),
-                 idesc_s, ks != 0 ? 1u : 0u);
+        const uint32_t sub = (uint32_t)(ks & 3) * 32;
+        umma_f16(tmem_base, umma_desc_sw128_kmajor(sbase + SM_Q + (uint32_t)(ks >> 2) * QPANEL + sub),
+                 umma_desc_sw128_kmajor(sbase + SM_K + stage * KTILE + (uint32_t)(ks >> 2) * KPANEL + sub), idesc_s,
+                 ks != 0 ? 1u : 0u);
       }
       umma_commit(mbar_s);
     }
@@ -124,29 +132,31 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
     mbar_wait(mbar_s, (uint32_t)j & 1u);
     tc_fence_after();
 
-    // ---- this thread's 64 columns of its S row
-    float s[64];
+    // ---- this thread's CPT columns of its S row
+    float s[CPT];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CPT / 16; ++c) {
       uint32_t raw[16];
-      tmem_ld16(lane_addr + half * 64 + c * 16, raw);
+      tmem_ld16(lane_addr + half * CPT + c * 16, raw);
 #pragma unroll
       for (int i = 0; i < 16; ++i) s[c * 16 + i] = __uint_as_float(raw[i]);
     }
     tmem_ld_wait();
-    const int kvalid = min(BKEY, nk - j * BKEY) - half * 64;   // valid columns among this thread's 64
-    if (kvalid < 64) {
+    const int kvalid = min(BKEY, nk - j * BKEY) - half * CPT;   // valid columns among this thread's
+    if (kvalid < CPT) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) if (i >= kvalid) s[i] = -1e30f;
+      for (int i = 0; i < CPT; ++i) if (i >= kvalid) s[i] = -1e30f;
     }
     float mx[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
 #pragma unroll
-    for (int i = 0; i < 64; i += 4) {
+    for (int i = 0; i < CPT; i += 4) {
       mx[0] = fmaxf(mx[0], s[i]); mx[1] = fmaxf(mx[1], s[i + 1]); mx[2] = fmaxf(mx[2], s[i + 2]); mx[3] = fmaxf(mx[3], s[i + 3]);
     }
-    xch[half * 128 + row] = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
+    // both threads of a row read the same two (fp16-rounded) values, so they agree on the reference max; any
+    // reference works for softmax as long as numerator and denominator share it
+    xmax[half * 128 + row] = __float2half_rn(fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2, -60000.f));
     __syncthreads();
-    const float m_tile = fmaxf(xch[row], xch[128 + row]);
+    const float m_tile = fmaxf(__half2float(xmax[row]), __half2float(xmax[128 + row]));
     const float m_new = fmaxf(m_run, m_tile);
     int need = 0;
     if (j == 0) m_used = m_new;
@@ -159,18 +169,18 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[16];
-        tmem_ld16(lane_addr + 128 + half * 64 + c * 16, raw);
+        tmem_ld16(lane_addr + O_COL + half * 64 + c * 16, raw);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * f);
-        tmem_st16(lane_addr + 128 + half * 64 + c * 16, raw);
+        tmem_st16(lane_addr + O_COL + half * 64 + c * 16, raw);
       }
       tmem_st_wait();
     }
-    // ---- P = exp2(s*scale - m_used) -> shared memory (A operand of P.V): this thread's 8 x 16-byte chunks
+    // ---- P = exp2(s*scale - m_used) -> shared memory (A operand of P.V): this thread's 16-byte chunks
     float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
+    for (int ch = 0; ch < CPT / 8; ++ch) {
       __align__(16) __half2 h[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
         ps[e] += a + b;
         h[e] = __floats2half2_rn(a, b);
       }
-      *reinterpret_cast<uint4*>(smem + SM_P + tile_off(row, half * 8 + ch)) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(smem + SM_P + tile_off(QPANEL, row, half * (CPT / 8) + ch)) = *reinterpret_cast<uint4*>(h);
     }
     row_sum += (ps[0] + ps[1]) + (ps[2] + ps[3]);
     fence_proxy_async();
@@ -188,10 +198,10 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
     if (tid == 0) {   // O += P V
       tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t adesc = umma_desc_sw128_kmajor(sbase + SM_P + (uint32_t)(ks >> 2) * PANEL + (uint32_t)(ks & 3) * 32);
-        const uint64_t bdesc = umma_desc_sw128_mnmajor(sbase + SM_V + stage * TILE + (uint32_t)ks * 2048, PANEL);
-        umma_f16(tmem_base + 128, adesc, bdesc, idesc_o, (j | ks) != 0 ? 1u : 0u);
+      for (int ks = 0; ks < BKEY / 16; ++ks) {
+        const uint64_t adesc = umma_desc_sw128_kmajor(sbase + SM_P + (uint32_t)(ks >> 2) * QPANEL + (uint32_t)(ks & 3) * 32);
+        const uint64_t bdesc = umma_desc_sw128_mnmajor(sbase + SM_V + stage * KTILE + (uint32_t)ks * 2048, KPANEL);
+        umma_f16(tmem_base + O_COL, adesc, bdesc, idesc_o, (j | ks) != 0 ? 1u : 0u);
       }
       umma_commit(mbar_o);
     }
@@ -200,9 +210,9 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
   // ---- epilogue: O / row_sum -> global (unpadded grid; padding queries are dropped)
   mbar_wait(mbar_o, (uint32_t)(ntiles - 1) & 1u);
   tc_fence_after();
-  xch[half * 128 + row] = row_sum;
+  xsum[half * 128 + row] = row_sum;
   __syncthreads();
-  const float inv = 1.f / (xch[row] + xch[128 + row]);
+  const float inv = 1.f / (xsum[row] + xsum[128 + row]);
   const int qi = q0 + row;
   bool store = qi < nq;
   __half* dst = nullptr;
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t raw[16];
-    tmem_ld16(lane_addr + 128 + half * 64 + c * 16, raw);
+    tmem_ld16(lane_addr + O_COL + half * 64 + c * 16, raw);
     tmem_ld_wait();
     if (store) {
       __align__(16) __half2 h[8];
@@ -229,16 +239,17 @@ __global__ void __launch_bounds__(NT, 1) window_attention_tc(const PPAttnParams 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace
 
 int pp_launch_attention_tc(const PPAttnParams& p, int n_sliding, int t_max, cudaStream_t st) {
-  const size_t smem = SM_END + 1024 + 64 + 2 * 128 * sizeof(float);
+  const size_t smem = SM_END + 64 + 2 * 128 * sizeof(__half);   // 115,264 B: two CTAs per SM
   static bool attr_set = false;
   if (!attr_set) {
     PP_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PP_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   dim3 grid(pp_ceil_div(t_max * WIN_TOK, BQ), p.n_win * 4, n_sliding);
