@@ -130,7 +130,7 @@ def run_b200(args, rank, world):
     import torch.distributed as dist
     from comfyui_propainter_nodes_b200 import weights as Wt
     from comfyui_propainter_nodes_b200 import propainter_inference as PI
-    from comfyui_propainter_nodes_b200.propainter_nodes import ProPainterInpaint
+    from comfyui_propainter_nodes_b200.propainter_nodes import ProPainterInpaint, _to_host
     from comfyui_propainter_nodes_b200.utils import image_utils as IU
     from comfyui_propainter_nodes_b200.utils import model_utils as MU
 
@@ -211,7 +211,7 @@ def run_b200(args, rank, world):
         if strong:   # host tensors -> device pre-processing -> sharded clip -> float IMAGE back on the host
             from comfyui_propainter_nodes_b200.parallel import inpaint_clip_distributed
             f, m1, m2, o = eng.preprocess(img_host, mask_host, PARAMS["flow_mask_dilates"], PARAMS["mask_dilates"])
-            return eng.postprocess(inpaint_clip_distributed(models, f, m1, m2, o, cfg)).cpu()
+            return _to_host(eng.postprocess(inpaint_clip_distributed(models, f, m1, m2, o, cfg)))
         with contextlib.redirect_stdout(sys.stderr):   # the node prints progress; stdout carries only the JSON line
             frames, _, _ = node.propainter_inpainting(img_host, mask_host, WIDTH, HEIGHT, **PARAMS)
         return frames

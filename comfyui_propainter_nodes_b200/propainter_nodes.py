@@ -64,8 +64,20 @@ def _run(models, frames_t, flow_masks_t, masks_dilated_t, originals_u8, cfg: Pro
     updated_frames, updated_masks, flows = process_inpainting(models, frames_t, flow_masks_t, masks_dilated_t, cfg)
     comp = feature_propagation_device(models.inpaint_model, updated_frames, updated_masks, masks_dilated_t, flows,
                                       originals_u8, cfg)
-    images = models.inpaint_model.engine.postprocess(comp).cpu()   # IMAGE stays a CPU tensor like the reference's
+    images = _to_host(models.inpaint_model.engine.postprocess(comp))   # IMAGE stays a CPU tensor like the reference's
     return images, flow_masks_t.squeeze(), masks_dilated_t.squeeze()
+
+
+def _to_host(dev: torch.Tensor) -> torch.Tensor:
+    """Device -> host copy of the IMAGE result into page-locked memory from torch's caching host allocator.
+
+    A fresh pageable 221 MB tensor (80 frames 640x360 float32) costs 60-90 ms of page faults per call on the GPU
+    host (measured, tools/e2e_breakdown.py); a pinned block is recycled by the allocator once the previous result
+    has been released, never while a caller still holds it, and the copy runs at PCIe rate."""
+    host = torch.empty(dev.shape, dtype=dev.dtype, device="cpu", pin_memory=True)
+    host.copy_(dev, non_blocking=True)
+    torch.cuda.current_stream(dev.device).synchronize()
+    return host
 
 
 class ProPainterInpaint:
