@@ -1,0 +1,136 @@
+// Epilogue shared by the tcgen05 conv kernels: 16 consecutive output channels of one output pixel
+// (accumulators already in registers) -> bias / activation / residual / GRU gate fusions -> global memory.
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace ppconv {
+
+template <int ACT>
+__device__ __forceinline__ void act16_t(float (&v)[16], float slope) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (ACT == PP_ACT_RELU) v[i] = fmaxf(v[i], 0.f);
+    else if (ACT == PP_ACT_LRELU) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+    else if (ACT == PP_ACT_SIGMOID) v[i] = ppx::sigmoidf_(v[i]);
+    else if (ACT == PP_ACT_TANH) v[i] = tanhf(v[i]);
+    else if (ACT == PP_ACT_GELU) v[i] = ppx::gelu_erf(v[i]);
+  }
+}
+// one (uniform) branch per 16 values instead of one per value
+__device__ __forceinline__ void act16(float (&v)[16], int act, float slope) {
+  switch (act) {
+    case PP_ACT_RELU: act16_t<PP_ACT_RELU>(v, slope); break;
+    case PP_ACT_LRELU: act16_t<PP_ACT_LRELU>(v, slope); break;
+    case PP_ACT_SIGMOID: act16_t<PP_ACT_SIGMOID>(v, slope); break;
+    case PP_ACT_TANH: act16_t<PP_ACT_TANH>(v, slope); break;
+    case PP_ACT_GELU: act16_t<PP_ACT_GELU>(v, slope); break;
+    default: break;
+  }
+}
+
+// 16 consecutive fp16 values <-> registers.  `vec` (uniform per launch, checked on the host) says that full
+// runs are 16-byte aligned, so they move as 2 x 16-byte accesses; partial runs take the scalar tail.
+__device__ __forceinline__ void load16(const __half* src, int nvalid, bool vec, float (&r)[16]) {
+  if (vec && nvalid == 16) {
+    const uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
+    const __half2* ha = reinterpret_cast<const __half2*>(&a);
+    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fa = __half22float2(ha[i]), fb = __half22float2(hb[i]);
+      r[2 * i] = fa.x; r[2 * i + 1] = fa.y; r[8 + 2 * i] = fb.x; r[8 + 2 * i + 1] = fb.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = i < nvalid ? __half2float(src[i]) : 0.f;
+  }
+}
+__device__ __forceinline__ void store16(__half* dst, int nvalid, bool vec, const float (&v)[16]) {
+  if (vec && nvalid == 16) {
+    __align__(16) __half2 h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
+    reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = __float2half_rn(v[i]);
+  }
+}
+
+// `raw`: 16 fp32 accumulators (TMEM columns ng0-n0 .. +15) of output pixel `mrow` (flattened N*OH*OW index),
+// group g, first channel ng0 (within the group; ng0 < Cout_g).  `epi`/`vec` are launch-uniform.
+__device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uint32_t (&raw)[16], long long mrow, int g,
+                                                int ng0, int epi, bool vec) {
+    const int nvalid = min(16, p.Cout_g - ng0);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+    if (p.bias != nullptr) {
+      const float* bp = p.bias + g * p.Cout_g + ng0;
+      if (vec && nvalid == 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + i);
+          v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nvalid) v[i] += __ldg(bp + i);
+      }
+    }
+    if (epi == PP_EPI_STD) {
+      act16(v, p.act1, p.slope);
+      if (p.scale != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+      }
+      if (p.aux0 != nullptr) {
+        float r[16];
+        load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += r[i];
+      }
+      act16(v, p.act2, p.slope);
+      const long long o = mrow * p.out_cstride + p.out_coff + (long long)g * p.out_gstep + ng0;
+      if (p.out_fp32) {
+        float* dst = reinterpret_cast<float*>(p.out) + o;
+        if (vec && nvalid == 16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < nvalid) dst[i] = v[i];
+        }
+      } else {
+        store16(reinterpret_cast<__half*>(p.out) + o, nvalid, vec, v);
+      }
+    } else if (epi == PP_EPI_GRU_ZR) {
+      const int half_c = p.Cout_g >> 1;
+      act16_t<PP_ACT_SIGMOID>(v, 0.f);
+      if (ng0 < half_c) {
+        store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v);
+      } else {
+        const int c = ng0 - half_c;
+        float h[16];
+        load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, vec, h);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= h[i];
+        store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, vec, v);
+      }
+    } else {  // PP_EPI_GRU_H
+      float h[16], z[16];
+      load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, h);
+      load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, vec, z);
+      act16_t<PP_ACT_TANH>(v, 0.f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * v[i];
+      store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v);
+    }
+}
+
+}  // namespace ppconv

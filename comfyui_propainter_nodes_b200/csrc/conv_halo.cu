@@ -1,0 +1,365 @@
+// Halo-tile tcgen05 convolution for sm_100a: stride-1 convolutions whose A operand is fed by TMA.
+//
+// The implicit-GEMM kernel (conv_igemm.cu) fetches every input element once per filter tap (9x for a 3x3) with
+// cp.async and streams the weight tile once per 128 output pixels; on the 3x3 / 1x5 / 5x1 layers with <= 256
+// output channels that makes it L2->SM fill and instruction-issue bound.  Here one CTA tile is 16 rows x (8*MT)
+// columns of output pixels (MT = 1 or 2 sub-tiles of 128 pixels):
+//   * per 64-channel chunk, ONE 4-D TMA box load (cp.async.bulk.tensor, SWIZZLE_128B, out-of-image coordinates
+//     zero-filled = the conv's zero padding) lands the input patch [(16+(kh-1)dh) x (8MT+(kw-1)dw)] pixels x 128 B
+//     in shared memory; the A operand of filter tap (ky,kx) of sub-tile s is a *shifted view* of that patch:
+//     UMMA descriptor start = patch + ((ky*dh)*BW + kx*dw + 8s)*128 B, stride between 8-pixel row groups
+//     (SBO) = BW*128 B.  The 128B swizzle is a function of the absolute shared-memory address, so views that are
+//     not 1024-byte aligned are consistent with what TMA wrote (verified on B200: tools/umma_probe.cu).
+//   * the weight tile of (chunk, tap) [BN x 64] is streamed once per tile with cp.async.bulk and feeds both
+//     sub-tiles, so weights move once per 256 output pixels.
+// L2->SM bytes per output pixel drop ~3x on a 3x3 Cin=256 Cout=128 layer and no thread issues per-element loads.
+//
+// Warp roles (352 threads, one persistent CTA per SM): warps 0-7 epilogue (TMEM -> registers -> fused epilogue of
+// conv_epilogue.cuh -> global), warp 8 patch producer (TMA), warp 9 weight producer (bulk copy), warp 10 MMA issuer
+// + TMEM allocation.  Two accumulator sets in TMEM (2 x MT x BN columns) overlap epilogue i with main loop i+1.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "conv_epilogue.cuh"
+#include "conv_igemm.cuh"
+
+namespace {
+
+constexpr int NUM_THREADS = 352;
+constexpr int NUM_EPI_THREADS = 256;
+constexpr int WARP_A = 8, WARP_B = 9, WARP_MMA = 10;
+constexpr int MAX_SA = 4, MAX_SB = 8;
+constexpr int SMEM_BUDGET = 208 * 1024;
+
+struct HaloParams {
+  PPConvParams c;
+  CUtensorMap tmap[4];
+  int MT;            // sub-tiles (128 pixels each) per CTA tile
+  int BW, BH;        // patch size in pixels
+  int tiles_x, tiles_y, n_tiles;
+  int a_stage_bytes, b_stage_bytes, SA, SB;
+  int accw;          // TMEM columns per accumulator
+  int chunks;        // Cin / 64
+};
+
+__device__ __forceinline__ uint64_t desc_a_view(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(ppx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+struct TileCoord {
+  int n_idx, tx, ty, img, g;
+};
+__device__ __forceinline__ TileCoord decode_tile(const HaloParams& h, int tile) {
+  TileCoord t;
+  t.n_idx = tile % h.n_tiles;
+  int r = tile / h.n_tiles;
+  t.tx = r % h.tiles_x; r /= h.tiles_x;
+  t.ty = r % h.tiles_y; r /= h.tiles_y;
+  t.img = r % h.c.N;
+  t.g = r / h.c.N;
+  return t;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams h) {
+  using namespace ppx;
+  const PPConvParams& p = h.c;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_b = smem + h.SA * h.a_stage_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + h.SB * h.b_stage_bytes);
+  uint64_t* a_empty = a_full + MAX_SA;
+  uint64_t* b_full = a_empty + MAX_SA;
+  uint64_t* b_empty = b_full + MAX_SB;
+  uint64_t* acc_full = b_empty + MAX_SB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * p.N * p.groups;
+  const int taps = p.kh * p.kw;
+  const uint32_t set_cols = (uint32_t)(h.MT * h.accw);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2 * set_cols) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < h.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < h.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], NUM_EPI_THREADS); }
+    mbar_fence_init();
+  }
+  if (warp == WARP_MMA) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int r = quarter * 32 + lane;          // row of the 128-pixel sub-tile: 16 rows x 8 columns
+    const int epi = p.epi;
+    const bool vec = p.vec_ok != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(h, tile);
+      const int n0 = t.n_idx * p.BN;
+      const int bnt = min(p.BN, p.Cout_g_pad - n0);
+      const int set = it & 1;
+      // MT == 2: warps 0-3 own sub-tile 0, warps 4-7 sub-tile 1.  MT == 1: the two halves split the columns.
+      int sub = 0, c_lo = 0, c_hi = bnt;
+      if (h.MT == 2) sub = half;
+      else {
+        const int split = ((bnt / 16 + 1) / 2) * 16;
+        c_lo = half ? split : 0;
+        c_hi = half ? bnt : split;
+      }
+      const int oy = t.ty * 16 + (r >> 3), ox = t.tx * (8 * h.MT) + 8 * sub + (r & 7);
+      const bool mvalid = oy < p.OH && ox < p.OW;
+      const long long mrow = ((long long)t.img * p.OH + oy) * p.OW + ox;
+      mbar_wait(&acc_full[set], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + lane_base + set * set_cols + sub * h.accw;
+      bool released = false;
+      for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(t_row + c0, raw);
+        tmem_ld_wait();
+        if (c0 + 16 >= c_hi) {   // last read of this accumulator set by this thread: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[set]);
+          released = true;
+        }
+        const int ng0 = n0 + c0;
+        if (!mvalid || ng0 >= p.Cout_g) continue;
+        ppconv::conv_epilogue16(p, raw, mrow, t.g, ng0, epi, vec);
+      }
+      if (!released) {
+        tc_fence_before();
+        mbar_arrive(&acc_empty[set]);
+      }
+    }
+  } else if (warp == WARP_A) {
+    // ------------------------------------------------------------------ input patch producer (TMA)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = (uint32_t)(h.BW * h.BH * 128);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(h, tile);
+        const int x0 = t.tx * (8 * h.MT) - p.pw, y0 = t.ty * 16 - p.ph;
+        for (int c = 0; c < h.chunks; ++c) {
+          const int ci = c * 64;
+          int q = 0;
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            if (k < p.nseg && ci >= p.seg[k].cbegin) q = k;
+          const int ch0 = t.g * p.seg[q].gstep + (ci - p.seg[q].cbegin);
+          mbar_wait(&a_empty[s], phase ^ 1);
+          mbar_arrive_expect_tx(&a_full[s], bytes);
+          tma_load_4d(smem_u32(smem + s * h.a_stage_bytes), &h.tmap[q], ch0, x0, y0, t.img, &a_full[s]);
+          if (++s == h.SA) { s = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == WARP_B) {
+    // ------------------------------------------------------------------ weight tile producer (bulk copy)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(h, tile);
+        const int n0 = t.n_idx * p.BN;
+        const uint32_t bytes = (uint32_t)(min(p.BN, p.Cout_g_pad - n0) * 128);
+        const __half* wbase = p.wpacked + ((long long)t.g * p.num_kc * p.Cout_g_pad + n0) * 64;
+        for (int c = 0; c < h.chunks; ++c) {
+          for (int tap = 0; tap < taps; ++tap) {
+            const int kc = tap * h.chunks + c;
+            mbar_wait(&b_empty[s], phase ^ 1);
+            mbar_arrive_expect_tx(&b_full[s], bytes);
+            bulk_g2s(smem_u32(smem_b + s * h.b_stage_bytes), wbase + (long long)kc * p.Cout_g_pad * 64, bytes, &b_full[s]);
+            if (++s == h.SB) { s = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int sa = 0, sb = 0, it = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t sbo = (uint32_t)h.BW * 128;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int n0 = (tile % h.n_tiles) * p.BN;
+        const uint32_t idesc = umma_idesc_f16(128, (uint32_t)min(p.BN, p.Cout_g_pad - n0));
+        const int set = it & 1;
+        mbar_wait(&acc_empty[set], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + set * set_cols;
+        for (int c = 0; c < h.chunks; ++c) {
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + sa * h.a_stage_bytes);
+          int ky = 0, kx = 0;
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t a_tap = a_base + (uint32_t)((ky * p.dh) * h.BW + kx * p.dw) * 128;
+            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + sb * h.b_stage_bytes));
+            for (int sub = 0; sub < h.MT; ++sub) {
+              const uint64_t adesc = desc_a_view(a_tap + sub * 1024, sbo);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_addr + sub * h.accw, adesc + 2 * k, bdesc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&b_empty[sb]);
+            if (++sb == h.SB) { sb = 0; pb ^= 1; }
+            if (++kx == p.kw) { kx = 0; ++ky; }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == h.SA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&acc_full[set]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult qr;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// 0 = not eligible (caller falls back to the cp.async implicit-GEMM kernel), 1 = eligible.
+int pp_conv_halo_eligible(const PPConvParams& p) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("PP_CONV_HALO");
+    enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled) return 0;
+  if (p.sh != 1 || p.sw != 1 || p.pad_replicate) return 0;
+  if (p.Cin % 64 != 0) return 0;
+  if (p.kh * p.kw == 1) return 0;                    // 1x1: nothing to reuse (kept on the cp.async kernel for now)
+  for (int i = 0; i < p.nseg; ++i)
+    if (p.seg[i].cbegin % 64 != 0 || p.seg[i].cend % 64 != 0) return 0;
+  if ((p.kw - 1) * p.dw + 16 > 256 || (p.kh - 1) * p.dh + 16 > 256) return 0;
+  if ((long long)p.N * p.OH * p.OW < 128) return 0;
+  return encode_fn() != nullptr ? 1 : 0;
+}
+
+int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
+  HaloParams h;
+  h.c = pin;
+  PPConvParams& p = h.c;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    PP_CUDA_CHECK(cudaGetDevice(&dev));
+    PP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  }
+  // N tile: <= 128 columns (two accumulator sets x two sub-tiles fill the 512 TMEM columns)
+  const int n_tiles0 = pp_ceil_div(p.Cout_g_pad, 128);
+  int bn = pp_ceil_div(pp_ceil_div(p.Cout_g_pad, n_tiles0), 16) * 16;
+  const int tiles_y = pp_ceil_div(p.OH, 16);
+  auto count = [&](int mt, int bn_) {
+    return (long long)pp_ceil_div(p.Cout_g_pad, bn_) * pp_ceil_div(p.OW, 8 * mt) * tiles_y * p.N * p.groups;
+  };
+  int mt = 2;
+  if (count(2, bn) < num_sms) mt = 1;
+  while (count(mt, bn) < num_sms && bn >= 64 && bn % 32 == 0) bn /= 2;   // small launches: more, narrower tiles
+  p.BN = bn;
+  h.MT = mt;
+  h.BW = 8 * mt + (p.kw - 1) * p.dw;
+  h.BH = 16 + (p.kh - 1) * p.dh;
+  h.tiles_x = pp_ceil_div(p.OW, 8 * mt);
+  h.tiles_y = tiles_y;
+  h.n_tiles = pp_ceil_div(p.Cout_g_pad, bn);
+  h.chunks = p.Cin / 64;
+  h.accw = pp_ceil_div(bn, 32) * 32;
+  h.a_stage_bytes = pp_ceil_div(h.BW * h.BH * 128, 1024) * 1024;
+  h.b_stage_bytes = bn * 128;
+  int sa = 3, sb = 0;
+  for (; sa >= 2; --sa) {
+    sb = (SMEM_BUDGET - sa * h.a_stage_bytes) / h.b_stage_bytes;
+    if (sb >= 3) break;
+  }
+  PP_REQUIRE(sa >= 2 && sb >= 3, "conv_halo: patch %dx%d does not fit shared memory", h.BW, h.BH);
+  if (sb > MAX_SB) sb = MAX_SB;
+  if (sa == 3 && sb == MAX_SB && (SMEM_BUDGET - 4 * h.a_stage_bytes) / h.b_stage_bytes >= MAX_SB) sa = 4;
+  h.SA = sa; h.SB = sb;
+  const long long total_tiles = count(mt, bn);
+  PP_REQUIRE(total_tiles < (1LL << 31), "conv_halo: too many tiles");
+
+  EncodeTiledFn enc = encode_fn();
+  PP_REQUIRE(enc != nullptr, "conv_halo: cuTensorMapEncodeTiled is not available");
+  for (int i = 0; i < p.nseg; ++i) {
+    const PPConvSeg& s = p.seg[i];
+    const cuuint64_t cacc = (cuuint64_t)(p.groups - 1) * s.gstep + (s.cend - s.cbegin);
+    cuuint64_t dims[4] = {cacc, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)s.cstride * 2, (cuuint64_t)p.W * s.cstride * 2, (cuuint64_t)p.H * p.W * s.cstride * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)h.BW, (cuuint32_t)h.BH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&h.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(s.ptr + s.coff), dims, strides, box,
+                           es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PP_REQUIRE(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled failed (%d) for segment %d (cstride=%d W=%d H=%d N=%d)",
+               (int)r, i, s.cstride, p.W, p.H, p.N);
+  }
+  const size_t smem = (size_t)sa * h.a_stage_bytes + (size_t)sb * h.b_stage_bytes + 1024 + 512;
+  const int grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel, h));
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}

@@ -52,3 +52,7 @@ struct PPConvParams {
 };
 
 int pp_launch_conv(const PPConvParams& p, cudaStream_t stream);
+// conv_halo.cu: TMA halo-tile kernel for stride-1 convolutions (dispatched from pp_launch_conv when eligible;
+// PP_CONV_HALO=0 in the environment disables it).  `p` must already carry num_kc / vec_ok.
+int pp_conv_halo_eligible(const PPConvParams& p);
+int pp_launch_conv_halo(const PPConvParams& p, cudaStream_t stream);

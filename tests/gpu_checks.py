@@ -61,6 +61,11 @@ CONV_CASES = {
     "conv1x5": (1, 45, 80, 384, 256, 1, 5, 1, (0, 2), 1, 1, 0, E.ACT_SIGMOID, 0.0, False, None),
     "conv5x1_tanh": (1, 45, 80, 384, 128, 5, 1, 1, (2, 0), 1, 1, 0, E.ACT_TANH, 0.0, False, None),
     "k2304": (1, 45, 80, 2304, 128, 1, 1, 1, 0, 1, 1, 0, E.ACT_NONE, 0.0, False, None),
+    # TMA halo-tile kernel (conv_halo.cu): 16x16 tiles (MT=2), odd sizes with MT=1 + narrowed N tiles, two N tiles
+    "halo_mt2_64_64": (3, 90, 160, 64, 64, 3, 3, 1, 1, 1, 1, 0, E.ACT_LRELU, 0.2, True, None),
+    "halo_odd_size": (2, 37, 53, 192, 96, 3, 3, 1, 1, 1, 1, 0, E.ACT_RELU, 0.0, False, None),
+    "halo_mt2_256_192": (8, 45, 80, 256, 192, 3, 3, 1, 1, 1, 1, 0, E.ACT_NONE, 0.0, True, None),
+    "halo_5x5_dil2": (4, 48, 64, 64, 128, 5, 5, 1, 4, 2, 1, 0, E.ACT_NONE, 0.0, False, None),
 }
 
 

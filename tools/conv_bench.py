@@ -18,6 +18,13 @@ CASES = {
     "gen.decoder.4 (3x3, 64->64 @360x640)": (11, 360, 640, 64, 64, 3, 3, 1, 1),
     "tf.qkv (512->1536)": (1, 1, 29160, 512, 1536, 1, 1, 1, 1),
     "tf.fc1 (512->1960)": (1, 1, 29160, 512, 1960, 1, 1, 1, 1),
+    "raft.update.conv (3x3, 256->126)": (79, 45, 80, 256, 126, 3, 3, 1, 1),
+    "raft.gru.q (1x5, 384->128)": (79, 45, 80, 384, 128, 1, 5, 1, 1),
+    "raft.convf2 (3x3, 128->64)": (79, 45, 80, 128, 64, 3, 3, 1, 1),
+    "gen.fp.offset.3 (3x3, 128->432 @90x160 x5)": (5, 90, 160, 128, 432, 3, 3, 1, 1),
+    "gen.fp.backbone (3x3, 128->128 @90x160 x5)": (5, 90, 160, 128, 128, 3, 3, 1, 1),
+    "gen.encoder.10 (3x3 g2, 640->512 @90x160)": (16, 90, 160, 640, 512, 3, 3, 1, 2),
+    "rfc.offset.0 (3x3, 384->128, M=7200)": (2, 45, 80, 384, 128, 3, 3, 1, 1),
     "step conv (3x3, 128->128, M=7200)": (2, 45, 80, 128, 128, 3, 3, 1, 1),
     "step conv (3x3, 128->128, M=14400)": (1, 90, 160, 128, 128, 3, 3, 1, 1),
 }
