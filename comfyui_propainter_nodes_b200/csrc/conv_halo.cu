@@ -41,6 +41,10 @@ struct HaloParams {
   int a_stage_bytes, b_stage_bytes, SA, SB;
   int accw;          // TMEM columns per accumulator
   int chunks;        // Cin / 64
+  int flat;          // 1x1 convs: tiles are runs of 128*MT consecutive pixels of the flattened [N*H*W] pixel list
+  int n_img;         // images the tile index decomposes over (1 in flat mode)
+  int sub_bytes;     // A-view offset between the sub-tiles: 8 pixels (spatial) or 128 pixels (flat)
+  int debug;         // bit 0: skip the epilogue math/stores (PP_CONV_NOEPI=1, mainloop-only timing experiments)
 };
 
 __device__ __forceinline__ uint64_t desc_a_view(uint32_t addr, uint32_t sbo_bytes) {
@@ -69,8 +73,8 @@ __device__ __forceinline__ TileCoord decode_tile(const HaloParams& h, int tile) 
   int r = tile / h.n_tiles;
   t.tx = r % h.tiles_x; r /= h.tiles_x;
   t.ty = r % h.tiles_y; r /= h.tiles_y;
-  t.img = r % h.c.N;
-  t.g = r / h.c.N;
+  t.img = r % h.n_img;
+  t.g = r / h.n_img;
   return t;
 }
 
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * p.N * p.groups;
+  const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * p.groups;
   const int taps = p.kh * p.kw;
   const uint32_t set_cols = (uint32_t)(h.MT * h.accw);
   uint32_t tmem_cols = 32;
@@ -134,27 +138,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         c_lo = half ? split : 0;
         c_hi = half ? bnt : split;
       }
-      const int oy = t.ty * 16 + (r >> 3), ox = t.tx * (8 * h.MT) + 8 * sub + (r & 7);
-      const bool mvalid = oy < p.OH && ox < p.OW;
-      const long long mrow = ((long long)t.img * p.OH + oy) * p.OW + ox;
+      bool mvalid;
+      long long mrow;
+      if (h.flat) {
+        mrow = ((long long)t.tx * h.MT + sub) * 128 + r;
+        mvalid = mrow < p.M_total;
+      } else {
+        const int oy = t.ty * 16 + (r >> 3), ox = t.tx * (8 * h.MT) + 8 * sub + (r & 7);
+        mvalid = oy < p.OH && ox < p.OW;
+        mrow = ((long long)t.img * p.OH + oy) * p.OW + ox;
+      }
       mbar_wait(&acc_full[set], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + lane_base + set * set_cols + sub * h.accw;
-      bool released = false;
-      for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(t_row + c0, raw);
+      const bool skip = !mvalid || (h.debug & 1);
+      // 32 columns per round: both TMEM loads are in flight before the single wait
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+        uint32_t raw0[16], raw1[16];
+        const bool two = c0 + 16 < c_hi;
+        tmem_ld16(t_row + c0, raw0);
+        if (two) tmem_ld16(t_row + c0 + 16, raw1);
         tmem_ld_wait();
-        if (c0 + 16 >= c_hi) {   // last read of this accumulator set by this thread: hand it back to the MMA warp
+        if (c0 + 32 >= c_hi) {   // last read of this accumulator set by this thread: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&acc_empty[set]);
-          released = true;
         }
-        const int ng0 = n0 + c0;
-        if (!mvalid || ng0 >= p.Cout_g) continue;
-        ppconv::conv_epilogue16(p, raw, mrow, t.g, ng0, epi, vec);
+        if (skip) continue;
+        if (n0 + c0 < p.Cout_g) ppconv::conv_epilogue16(p, raw0, mrow, t.g, n0 + c0, epi, vec);
+        if (two && n0 + c0 + 16 < p.Cout_g) ppconv::conv_epilogue16(p, raw1, mrow, t.g, n0 + c0 + 16, epi, vec);
       }
-      if (!released) {
+      if (c_lo >= c_hi) {
         tc_fence_before();
         mbar_arrive(&acc_empty[set]);
       }
@@ -167,7 +180,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
       const uint32_t bytes = (uint32_t)(h.BW * h.BH * 128);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(h, tile);
-        const int x0 = t.tx * (8 * h.MT) - p.pw, y0 = t.ty * 16 - p.ph;
+        const int x0 = h.flat ? t.tx * (128 * h.MT) : t.tx * (8 * h.MT) - p.pw, y0 = h.flat ? 0 : t.ty * 16 - p.ph;
         for (int c = 0; c < h.chunks; ++c) {
           const int ci = c * 64;
           int q = 0;
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     if (lane == 0) {
       int sa = 0, sb = 0, it = 0;
       uint32_t pa = 0, pb = 0;
-      const uint32_t sbo = (uint32_t)h.BW * 128;
+      const uint32_t sbo = h.flat ? 1024u : (uint32_t)h.BW * 128;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int n0 = (tile % h.n_tiles) * p.BN;
         const uint32_t idesc = umma_idesc_f16(128, (uint32_t)min(p.BN, p.Cout_g_pad - n0));
@@ -227,7 +240,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
             const uint32_t a_tap = a_base + (uint32_t)((ky * p.dh) * h.BW + kx * p.dw) * 128;
             const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + sb * h.b_stage_bytes));
             for (int sub = 0; sub < h.MT; ++sub) {
-              const uint64_t adesc = desc_a_view(a_tap + sub * 1024, sbo);
+              const uint64_t adesc = desc_a_view(a_tap + sub * h.sub_bytes, sbo);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16(d_addr + sub * h.accw, adesc + 2 * k, bdesc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
@@ -271,17 +284,26 @@ EncodeTiledFn encode_fn() {
 
 // 0 = not eligible (caller falls back to the cp.async implicit-GEMM kernel), 1 = eligible.
 int pp_conv_halo_eligible(const PPConvParams& p) {
-  static int enabled = -1;
+  static int enabled = -1, allow_1x1 = -1;
   if (enabled < 0) {
     const char* e = getenv("PP_CONV_HALO");
     enabled = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+    e = getenv("PP_HALO_1X1");
+    allow_1x1 = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
   if (!enabled) return 0;
   if (p.sh != 1 || p.sw != 1 || p.pad_replicate) return 0;
-  if (p.Cin % 64 != 0) return 0;
-  if (p.kh * p.kw == 1) return 0;                    // 1x1: nothing to reuse (kept on the cp.async kernel for now)
-  for (int i = 0; i < p.nseg; ++i)
-    if (p.seg[i].cbegin % 64 != 0 || p.seg[i].cend % 64 != 0) return 0;
+  const bool flat = p.kh * p.kw == 1;
+  if (flat) {
+    // 1x1 conv / linear layer: tiles are runs of consecutive pixels; a ragged channel tail is zero-filled by TMA
+    if (!allow_1x1 || p.ph != 0 || p.pw != 0 || p.groups != 1) return 0;
+  } else if (p.Cin % 64 != 0) {
+    return 0;   // packed K order is (tap, ci): 64-channel chunks must not straddle taps
+  }
+  for (int i = 0; i < p.nseg; ++i) {
+    if (p.seg[i].cbegin % 64 != 0) return 0;
+    if (p.seg[i].cend % 64 != 0 && !(flat && i == p.nseg - 1)) return 0;
+  }
   if ((p.kw - 1) * p.dw + 16 > 256 || (p.kh - 1) * p.dh + 16 > 256) return 0;
   if ((long long)p.N * p.OH * p.OW < 128) return 0;
   return encode_fn() != nullptr ? 1 : 0;
@@ -298,24 +320,30 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
     PP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     PP_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   }
+  const bool flat = p.kh * p.kw == 1;
   // N tile: <= 128 columns (two accumulator sets x two sub-tiles fill the 512 TMEM columns)
   const int n_tiles0 = pp_ceil_div(p.Cout_g_pad, 128);
   int bn = pp_ceil_div(pp_ceil_div(p.Cout_g_pad, n_tiles0), 16) * 16;
-  const int tiles_y = pp_ceil_div(p.OH, 16);
+  const int tiles_y = flat ? 1 : pp_ceil_div(p.OH, 16);
+  auto tiles_x = [&](int mt) { return flat ? (int)pp_ceil_div64(p.M_total, 128 * mt) : pp_ceil_div(p.OW, 8 * mt); };
+  const int n_img = flat ? 1 : p.N;
   auto count = [&](int mt, int bn_) {
-    return (long long)pp_ceil_div(p.Cout_g_pad, bn_) * pp_ceil_div(p.OW, 8 * mt) * tiles_y * p.N * p.groups;
+    return (long long)pp_ceil_div(p.Cout_g_pad, bn_) * tiles_x(mt) * tiles_y * n_img * p.groups;
   };
   int mt = 2;
   if (count(2, bn) < num_sms) mt = 1;
   while (count(mt, bn) < num_sms && bn >= 64 && bn % 32 == 0) bn /= 2;   // small launches: more, narrower tiles
   p.BN = bn;
   h.MT = mt;
-  h.BW = 8 * mt + (p.kw - 1) * p.dw;
-  h.BH = 16 + (p.kh - 1) * p.dh;
-  h.tiles_x = pp_ceil_div(p.OW, 8 * mt);
+  h.flat = flat ? 1 : 0;
+  h.n_img = n_img;
+  h.BW = flat ? 128 * mt : 8 * mt + (p.kw - 1) * p.dw;
+  h.BH = flat ? 1 : 16 + (p.kh - 1) * p.dh;
+  h.sub_bytes = flat ? 128 * 128 : 8 * 128;
+  h.tiles_x = tiles_x(mt);
   h.tiles_y = tiles_y;
   h.n_tiles = pp_ceil_div(p.Cout_g_pad, bn);
-  h.chunks = p.Cin / 64;
+  h.chunks = pp_ceil_div(p.Cin, 64);
   h.accw = pp_ceil_div(bn, 32) * 32;
   h.a_stage_bytes = pp_ceil_div(h.BW * h.BH * 128, 1024) * 1024;
   h.b_stage_bytes = bn * 128;
@@ -328,6 +356,7 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
   if (sb > MAX_SB) sb = MAX_SB;
   if (sa == 3 && sb == MAX_SB && (SMEM_BUDGET - 4 * h.a_stage_bytes) / h.b_stage_bytes >= MAX_SB) sa = 4;
   h.SA = sa; h.SB = sb;
+  { const char* e = getenv("PP_CONV_NOEPI"); h.debug = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
   const long long total_tiles = count(mt, bn);
   PP_REQUIRE(total_tiles < (1LL << 31), "conv_halo: too many tiles");
 
@@ -339,6 +368,10 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
     cuuint64_t dims[4] = {cacc, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)s.cstride * 2, (cuuint64_t)p.W * s.cstride * 2, (cuuint64_t)p.H * p.W * s.cstride * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)h.BW, (cuuint32_t)h.BH, 1};
+    if (flat) {   // pixels as one flat dimension; the last tile's tail is out of bounds -> zero-filled
+      dims[1] = (cuuint64_t)p.M_total; dims[2] = 1; dims[3] = 1;
+      strides[1] = strides[2] = (cuuint64_t)p.M_total * s.cstride * 2;
+    }
     cuuint32_t es[4] = {1, 1, 1, 1};
     const CUresult r = enc(&h.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(s.ptr + s.coff), dims, strides, box,
                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

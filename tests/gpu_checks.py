@@ -65,6 +65,8 @@ CONV_CASES = {
     "halo_mt2_64_64": (3, 90, 160, 64, 64, 3, 3, 1, 1, 1, 1, 0, E.ACT_LRELU, 0.2, True, None),
     "halo_odd_size": (2, 37, 53, 192, 96, 3, 3, 1, 1, 1, 1, 0, E.ACT_RELU, 0.0, False, None),
     "halo_mt2_256_192": (8, 45, 80, 256, 192, 3, 3, 1, 1, 1, 1, 0, E.ACT_NONE, 0.0, True, None),
+    "halo_flat_328_256": (1, 45, 80, 324, 256, 1, 1, 1, 0, 1, 1, 0, E.ACT_RELU, 0.0, False, 328),
+    "halo_flat_ragged_rows": (1, 1, 2999, 512, 1960, 1, 1, 1, 0, 1, 1, 0, E.ACT_GELU, 0.0, True, None),
     "halo_5x5_dil2": (4, 48, 64, 64, 128, 5, 5, 1, 4, 2, 1, 0, E.ACT_NONE, 0.0, False, None),
 }
 
@@ -95,6 +97,7 @@ def check_conv(name):
     elif act == E.ACT_LRELU: ref = F.leaky_relu(ref, slope)
     elif act == E.ACT_SIGMOID: ref = torch.sigmoid(ref)
     elif act == E.ACT_TANH: ref = torch.tanh(ref)
+    elif act == E.ACT_GELU: ref = F.gelu(ref)
     if use_res:
         res = torch.randn(ref.shape, generator=g).permute(0, 2, 3, 1).contiguous().half().to(DEV)
         ref = ref + res.float().permute(0, 3, 1, 2)

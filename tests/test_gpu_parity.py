@@ -28,7 +28,8 @@ def C():
 @pytest.mark.parametrize("name", ["linear_512_1536", "conv3x3_128_128_lrelu_res", "conv7x7_s2_3_64", "conv3x3_dil3",
                                   "conv5x5_s2_replicate", "grouped_g4", "cout2", "cout126", "cout432", "cin261",
                                   "conv7x7_s3_40_512", "conv1x5", "conv5x1_tanh", "k2304", "halo_mt2_64_64",
-                                  "halo_odd_size", "halo_mt2_256_192", "halo_5x5_dil2"])
+                                  "halo_odd_size", "halo_mt2_256_192", "halo_5x5_dil2", "halo_flat_328_256",
+                                  "halo_flat_ragged_rows"])
 def test_tcgen05_conv_matches_torch_fp32(C, name):
     s = C.check_conv(name)
     assert not s["nan"] and s["rel"] < 2e-3, s

@@ -18,6 +18,8 @@ CASES = {
     "gen.decoder.4 (3x3, 64->64 @360x640)": (11, 360, 640, 64, 64, 3, 3, 1, 1),
     "tf.qkv (512->1536)": (1, 1, 29160, 512, 1536, 1, 1, 1, 1),
     "tf.fc1 (512->1960)": (1, 1, 29160, 512, 1960, 1, 1, 1, 1),
+    "tf.qkv full (512->1536, M=445k)": (275, 30, 54, 512, 1536, 1, 1, 1, 1),
+    "tf.proj full (512->512, M=445k)": (275, 30, 54, 512, 512, 1, 1, 1, 1),
     "raft.update.conv (3x3, 256->126)": (79, 45, 80, 256, 126, 3, 3, 1, 1),
     "raft.gru.q (1x5, 384->128)": (79, 45, 80, 384, 128, 1, 5, 1, 1),
     "raft.convf2 (3x3, 128->64)": (79, 45, 80, 128, 64, 3, 3, 1, 1),
