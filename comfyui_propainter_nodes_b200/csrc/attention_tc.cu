@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(NT, 2) window_attention_tc(const PPAttnParams 
     cp_async_wait<0>();
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {   // S = Q K^T
+    if (warp == 0 && elect_one()) {   // S = Q K^T (one elected lane: ptxas emits each UTCHMMA once)
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NT, 2) window_attention_tc(const PPAttnParams 
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {   // O += P V
+    if (warp == 0 && elect_one()) {   // O += P V
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < BKEY / 16; ++ks) {

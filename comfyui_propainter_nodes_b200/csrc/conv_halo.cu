@@ -47,16 +47,6 @@ struct HaloParams {
   int debug;         // bit 0: skip the epilogue math/stores (PP_CONV_NOEPI=1, mainloop-only timing experiments)
 };
 
-__device__ __forceinline__ uint64_t desc_a_view(uint32_t addr, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
@@ -174,7 +164,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     }
   } else if (warp == WARP_A) {
     // ------------------------------------------------------------------ input patch producer (TMA)
-    if (lane == 0) {
+    if (ppx::elect_one()) {
       int s = 0;
       uint32_t phase = 0;
       const uint32_t bytes = (uint32_t)(h.BW * h.BH * 128);
@@ -197,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     }
   } else if (warp == WARP_B) {
     // ------------------------------------------------------------------ weight tile producer (bulk copy)
-    if (lane == 0) {
+    if (ppx::elect_one()) {
       int s = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -218,36 +208,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     }
   } else if (warp == WARP_MMA) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // One elected lane (elect.sync lets ptxas emit each tcgen05.mma once instead of a per-lane loop).  The loop is
+    // kept lean -- descriptors advance by precomputed 16-byte-unit steps -- because a single thread has to issue
+    // one UTCHMMA per 32-64 tensor-pipe cycles.
+    if (ppx::elect_one()) {
       int sa = 0, sb = 0, it = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t sbo = h.flat ? 1024u : (uint32_t)h.BW * 128;
+      const uint64_t a_hi = ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint64_t b_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint32_t a_base0 = (smem_u32(smem) & 0x3FFFF) >> 4, b_base0 = (smem_u32(smem_b) & 0x3FFFF) >> 4;
+      const uint32_t a_stage16 = (uint32_t)h.a_stage_bytes >> 4, b_stage16 = (uint32_t)h.b_stage_bytes >> 4;
+      const uint32_t step_x = (uint32_t)p.dw * 8;                                           // next tap in the row
+      const uint32_t step_row = (uint32_t)(p.dh * h.BW - (p.kw - 1) * p.dw) * 8;            // last tap of a row -> next row
+      const uint32_t sub16 = (uint32_t)h.sub_bytes >> 4;
+      const bool two = h.MT == 2;
+      const int kw = p.kw;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int n0 = (tile % h.n_tiles) * p.BN;
         const uint32_t idesc = umma_idesc_f16(128, (uint32_t)min(p.BN, p.Cout_g_pad - n0));
         const int set = it & 1;
         mbar_wait(&acc_empty[set], ((uint32_t)(it >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + set * set_cols;
+        const uint32_t d0 = tmem_base + set * set_cols, d1 = d0 + h.accw;
+        uint32_t accum = 0;
         for (int c = 0; c < h.chunks; ++c) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + sa * h.a_stage_bytes);
-          int ky = 0, kx = 0;
+          uint64_t adesc = a_hi | (uint64_t)(a_base0 + sa * a_stage16);
+          int kx = 0;
           for (int tap = 0; tap < taps; ++tap) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
-            const uint32_t a_tap = a_base + (uint32_t)((ky * p.dh) * h.BW + kx * p.dw) * 128;
-            const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem_b + sb * h.b_stage_bytes));
-            for (int sub = 0; sub < h.MT; ++sub) {
-              const uint64_t adesc = desc_a_view(a_tap + sub * h.sub_bytes, sbo);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d_addr + sub * h.accw, adesc + 2 * k, bdesc + 2 * k, idesc, (c | tap | k) != 0 ? 1u : 0u);
+            const uint64_t bdesc = b_hi | (uint64_t)(b_base0 + sb * b_stage16);
+            umma_f16(d0, adesc, bdesc, idesc, accum);
+            umma_f16(d0, adesc + 2, bdesc + 2, idesc, 1u);
+            umma_f16(d0, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_f16(d0, adesc + 6, bdesc + 6, idesc, 1u);
+            if (two) {
+              const uint64_t adesc1 = adesc + sub16;
+              umma_f16(d1, adesc1, bdesc, idesc, accum);
+              umma_f16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+              umma_f16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+              umma_f16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
             }
+            accum = 1u;
             umma_commit(&b_empty[sb]);
             if (++sb == h.SB) { sb = 0; pb ^= 1; }
-            if (++kx == p.kw) { kx = 0; ++ky; }
+            adesc += step_x;
+            if (++kx == kw) { kx = 0; adesc += step_row - step_x; }
           }
           umma_commit(&a_empty[sa]);
           if (++sa == h.SA) { sa = 0; pa ^= 1; }
@@ -255,6 +264,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         umma_commit(&acc_full[set]);
       }
     }
+    __syncwarp();
   }
 
   tc_fence_before();

@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
       }
     }
   } else if (warp == WARP_MMA) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (elect.sync: one UTCHMMA
+    // per tcgen05.mma instead of ptxas' per-lane loop around a uniform-datapath instruction)
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_f16(BM, p.BN);
       int s = 0, it = 0;
       uint32_t phase = 0;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
     }
   } else {
     // ------------------------------------------------------------------ weight-tile loader (TMA bulk copy)
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {

@@ -194,6 +194,19 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
 // same with the B operand MN-major (bit 16)
 __device__ __forceinline__ uint32_t umma_idesc_f16_bmn(uint32_t m, uint32_t n) { return umma_idesc_f16(m, n) | (1u << 16); }
 
+// true on exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
