@@ -217,7 +217,11 @@ def run_b200(args, rank, world):
         return frames
     e2e_value = None
     if not args.no_e2e:
-        e2e_step()
+        # two warm-up calls whose results are held the way a caller (ComfyUI's output cache) holds them: the IMAGE
+        # result lives in page-locked blocks of torch's caching host allocator, and the steady state alternates
+        # between two blocks (the previous result is released only after the next one exists)
+        res = e2e_step()
+        res = e2e_step()
         barrier()
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 3))
