@@ -59,10 +59,51 @@ __device__ __forceinline__ void store16(__half* dst, int nvalid, bool vec, const
   }
 }
 
+__device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (&r)[16]) {
+  const __half2* ha = reinterpret_cast<const __half2*>(&a);
+  const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __half22float2(ha[i]), fb = __half22float2(hb[i]);
+    r[2 * i] = fa.x; r[2 * i + 1] = fa.y; r[8 + 2 * i] = fb.x; r[8 + 2 * i + 1] = fb.y;
+  }
+}
+
+// Epilogue operands that do not depend on the accumulator (residual / GRU h and z), fetched while the TMEM read of
+// the same 16 columns is still in flight so the two latencies overlap instead of adding up.
+struct EpiAux {
+  uint4 a0[2], a1[2];
+  bool have;
+};
+__device__ __forceinline__ void conv_epilogue_prefetch16(const PPConvParams& p, long long mrow, int ng0, int epi, bool vec,
+                                                         EpiAux& x) {
+  x.have = false;
+  if (!vec || p.Cout_g - ng0 < 16) return;
+  const __half* s0 = nullptr;
+  const __half* s1 = nullptr;
+  if (epi == PP_EPI_STD) {
+    if (p.aux0 != nullptr) s0 = p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0;
+  } else if (epi == PP_EPI_GRU_ZR) {
+    const int half_c = p.Cout_g >> 1;
+    if (ng0 >= half_c) s0 = p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + (ng0 - half_c);
+  } else {
+    s0 = p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0;
+    s1 = p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0;
+  }
+  if (s0 == nullptr) return;
+  x.have = true;
+  x.a0[0] = reinterpret_cast<const uint4*>(s0)[0];
+  x.a0[1] = reinterpret_cast<const uint4*>(s0)[1];
+  if (s1 != nullptr) {
+    x.a1[0] = reinterpret_cast<const uint4*>(s1)[0];
+    x.a1[1] = reinterpret_cast<const uint4*>(s1)[1];
+  }
+}
+
 // `raw`: 16 fp32 accumulators (TMEM columns ng0-n0 .. +15) of output pixel `mrow` (flattened N*OH*OW index),
 // group g, first channel ng0 (within the group; ng0 < Cout_g).  `epi`/`vec` are launch-uniform.
 __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uint32_t (&raw)[16], long long mrow, int g,
-                                                int ng0, int epi, bool vec) {
+                                                int ng0, int epi, bool vec, const EpiAux* pre = nullptr) {
     const int nvalid = min(16, p.Cout_g - ng0);
     float v[16];
 #pragma unroll
@@ -89,7 +130,8 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
       }
       if (p.aux0 != nullptr) {
         float r[16];
-        load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, r);
+        if (pre != nullptr && pre->have) unpack16(pre->a0[0], pre->a0[1], r);
+        else load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, r);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += r[i];
       }
@@ -117,15 +159,21 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
       } else {
         const int c = ng0 - half_c;
         float h[16];
-        load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, vec, h);
+        if (pre != nullptr && pre->have) unpack16(pre->a0[0], pre->a0[1], h);
+        else load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, vec, h);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= h[i];
         store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, vec, v);
       }
     } else {  // PP_EPI_GRU_H
       float h[16], z[16];
-      load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, h);
-      load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, vec, z);
+      if (pre != nullptr && pre->have) {
+        unpack16(pre->a0[0], pre->a0[1], h);
+        unpack16(pre->a1[0], pre->a1[1], z);
+      } else {
+        load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, h);
+        load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, vec, z);
+      }
       act16_t<PP_ACT_TANH>(v, 0.f);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * v[i];

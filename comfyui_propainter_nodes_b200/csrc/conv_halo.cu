@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
     const int r = quarter * 32 + lane;          // row of the 128-pixel sub-tile: 16 rows x 8 columns
     const int epi = p.epi;
     const bool vec = p.vec_ok != 0;
+    const bool has_aux = p.aux0 != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(h, tile);
@@ -148,14 +149,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         const bool two = c0 + 16 < c_hi;
         tmem_ld16(t_row + c0, raw0);
         if (two) tmem_ld16(t_row + c0 + 16, raw1);
+        const bool do0 = !skip && n0 + c0 < p.Cout_g, do1 = !skip && two && n0 + c0 + 16 < p.Cout_g;
+        ppconv::EpiAux x0, x1;
+        x0.have = x1.have = false;
+        if (has_aux) {   // residual / GRU operands: issued while the TMEM reads are in flight
+          if (do0) ppconv::conv_epilogue_prefetch16(p, mrow, n0 + c0, epi, vec, x0);
+          if (do1) ppconv::conv_epilogue_prefetch16(p, mrow, n0 + c0 + 16, epi, vec, x1);
+        }
         tmem_ld_wait();
         if (c0 + 32 >= c_hi) {   // last read of this accumulator set by this thread: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&acc_empty[set]);
         }
-        if (skip) continue;
-        if (n0 + c0 < p.Cout_g) ppconv::conv_epilogue16(p, raw0, mrow, t.g, n0 + c0, epi, vec);
-        if (two && n0 + c0 + 16 < p.Cout_g) ppconv::conv_epilogue16(p, raw1, mrow, t.g, n0 + c0 + 16, epi, vec);
+        if (do0) ppconv::conv_epilogue16(p, raw0, mrow, t.g, n0 + c0, epi, vec, &x0);
+        if (do1) ppconv::conv_epilogue16(p, raw1, mrow, t.g, n0 + c0 + 16, epi, vec, &x1);
       }
       if (c_lo >= c_hi) {
         tc_fence_before();

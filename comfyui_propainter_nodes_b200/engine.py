@@ -249,6 +249,18 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
         expect = torch.from_numpy(Wspec.rolled_valid_indices())
         if not torch.equal(g[a + "valid_ind_rolled"].cpu().long(), expect):
             raise ValueError("checkpoint's valid_ind_rolled differs from the 5x9 window ring this engine implements")
+    # Layers whose input is [k*64 feature channels | a few mask/flow channels] (cat(cur, prop, mask) = 264 kernel
+    # channels): "<name>.main" covers the 64-aligned part (TMA halo-tile kernel, no bias) and "<name>.tail" the rest
+    # (+ bias); the call site runs tail -> partial sum, then main with the partial as residual.  conv(x) is linear in
+    # the channel split, so the sum is the same convolution.
+    for name in [n for n in convs if n.endswith((".offset.0", ".backbone.0", "fuse.0")) and n.startswith("gen.fp.")]:
+        w, b, groups, cmap = convs[name]
+        cmap = cmap if cmap is not None else list(range(w.shape[1]))
+        cut = len(cmap) // 64 * 64
+        if groups != 1 or cut == 0 or cut == len(cmap):
+            continue
+        convs[name + ".main"] = (w, None, 1, cmap[:cut])
+        convs[name + ".tail"] = (w, b, 1, cmap[cut:])
     return convs, tens
 
 
