@@ -28,6 +28,19 @@ __device__ __forceinline__ void act16(float (&v)[16], int act, float slope) {
   }
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): 16 fp16 channels of one pixel in ONE request, so a warp's
+// store touches each of its 32 rows' sectors once instead of twice.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // 16 consecutive fp16 values <-> registers.  `vec` (uniform per launch, checked on the host) says that full
 // runs are 16-byte aligned, so they move as 2 x 16-byte accesses; partial runs take the scalar tail.
 __device__ __forceinline__ void load16(const __half* src, int nvalid, bool vec, float (&r)[16]) {
@@ -45,11 +58,15 @@ __device__ __forceinline__ void load16(const __half* src, int nvalid, bool vec, 
     for (int i = 0; i < 16; ++i) r[i] = i < nvalid ? __half2float(src[i]) : 0.f;
   }
 }
-__device__ __forceinline__ void store16(__half* dst, int nvalid, bool vec, const float (&v)[16]) {
+__device__ __forceinline__ void store16(__half* dst, int nvalid, bool vec, const float (&v)[16], bool v32 = false) {
   if (vec && nvalid == 16) {
     __align__(16) __half2 h[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    if (v32) {
+      stg256(dst, reinterpret_cast<uint4*>(h)[0], reinterpret_cast<uint4*>(h)[1]);
+      return;
+    }
     reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<uint4*>(h)[0];
     reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<uint4*>(h)[1];
   } else {
@@ -92,6 +109,11 @@ __device__ __forceinline__ void conv_epilogue_prefetch16(const PPConvParams& p, 
   }
   if (s0 == nullptr) return;
   x.have = true;
+  if (p.vec32_ok) {
+    ldg256(s0, x.a0[0], x.a0[1]);
+    if (s1 != nullptr) ldg256(s1, x.a1[0], x.a1[1]);
+    return;
+  }
   x.a0[0] = reinterpret_cast<const uint4*>(s0)[0];
   x.a0[1] = reinterpret_cast<const uint4*>(s0)[1];
   if (s1 != nullptr) {
@@ -105,6 +127,7 @@ __device__ __forceinline__ void conv_epilogue_prefetch16(const PPConvParams& p, 
 __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uint32_t (&raw)[16], long long mrow, int g,
                                                 int ng0, int epi, bool vec, const EpiAux* pre = nullptr) {
     const int nvalid = min(16, p.Cout_g - ng0);
+    const bool v32 = p.vec32_ok != 0;
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
@@ -149,13 +172,13 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
             if (i < nvalid) dst[i] = v[i];
         }
       } else {
-        store16(reinterpret_cast<__half*>(p.out) + o, nvalid, vec, v);
+        store16(reinterpret_cast<__half*>(p.out) + o, nvalid, vec, v, v32);
       }
     } else if (epi == PP_EPI_GRU_ZR) {
       const int half_c = p.Cout_g >> 1;
       act16_t<PP_ACT_SIGMOID>(v, 0.f);
       if (ng0 < half_c) {
-        store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v);
+        store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v, v32);
       } else {
         const int c = ng0 - half_c;
         float h[16];
@@ -163,7 +186,7 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
         else load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + c, nvalid, vec, h);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] *= h[i];
-        store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, vec, v);
+        store16(p.out2 + mrow * p.out2_cstride + p.out2_coff + c, nvalid, vec, v, v32);
       }
     } else {  // PP_EPI_GRU_H
       float h[16], z[16];
@@ -177,7 +200,7 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
       act16_t<PP_ACT_TANH>(v, 0.f);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = (1.f - z[i]) * h[i] + z[i] * v[i];
-      store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v);
+      store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v, v32);
     }
 }
 

@@ -29,7 +29,7 @@ namespace {
 constexpr int NUM_THREADS = 352;
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int WARP_A = 8, WARP_B = 9, WARP_MMA = 10;
-constexpr int MAX_SA = 4, MAX_SB = 8;
+constexpr int MAX_SA = 4, MAX_SB = 16;
 constexpr int SMEM_BUDGET = 208 * 1024;
 
 struct HaloParams {

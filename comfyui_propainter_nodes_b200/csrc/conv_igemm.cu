@@ -265,6 +265,13 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
     if (p.bias != nullptr) ok = ok && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (p.groups == 1 || p.Cout_g % 4 == 0);
     if (p.epi == PP_EPI_GRU_ZR) ok = ok && ((p.Cout_g >> 1) % 16 == 0);
     p.vec_ok = ok ? 1 : 0;
+    auto al32 = [](const void* ptr, long long cs, long long co, long long gs) {
+      return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && cs % 16 == 0 && co % 16 == 0 && gs % 16 == 0);
+    };
+    p.vec32_ok = (ok && !p.out_fp32 && al32(p.out, p.out_cstride, p.out_coff, p.out_gstep) &&
+                  al32(p.aux0, p.aux0_cstride, p.aux0_coff, 0) && al32(p.aux1, p.aux1_cstride, p.aux1_coff, 0) &&
+                  al32(p.out2, p.out2_cstride, p.out2_coff, 0) && (p.epi != PP_EPI_GRU_ZR || ((p.Cout_g >> 1) % 16 == 0)))
+                     ? 1 : 0;
   }
   if (pp_conv_halo_eligible(p)) return pp_launch_conv_halo(p, stream);   // stride-1 k>1 layers: TMA halo-tile kernel
   const int stage_bytes = A_STAGE_BYTES + p.BN * 128;

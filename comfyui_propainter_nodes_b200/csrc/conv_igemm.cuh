@@ -42,6 +42,7 @@ struct PPConvParams {
   int Cout_g, Cout_g_pad, BN, groups;
   int stages;
   int vec_ok;             // set by the launcher: every epilogue pointer/stride allows 16-byte accesses on full runs
+  int vec32_ok;           // ... and fp16 epilogue operands are 32-byte aligned: one 256-bit access per 16 channels
   // epilogue
   int epi, act1, act2;
   float slope, scale;

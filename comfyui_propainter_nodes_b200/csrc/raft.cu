@@ -146,17 +146,32 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
   const int npairs = T - 1;
   const int bn_corr = P_pad / pp_ceil_div(P, 256);
 
-  for (int dir = 0; dir < 2; ++dir) {
-    for (int b0 = 0; b0 < npairs; b0 += max_pairs) {
-      const int B = (b0 + max_pairs <= npairs) ? max_pairs : npairs - b0;
+  // Both directions share one batch: pair slot s < npairs is the forward pair (s -> s+1), slot npairs + s the backward
+  // pair (s+1 -> s).  One launch per layer then covers 2(T-1) pairs (half as many launches and tile-quantisation
+  // tails on the 148 SMs as one batch per direction); only the steps that address frames (correlation, context
+  // split, final upsampling) run once per direction sub-range of the batch.
+  struct Sub { int dir, b0, cnt, off; };   // direction, first pair of that direction, count, slot offset in the batch
+  for (int s0 = 0; s0 < 2 * npairs; s0 += max_pairs) {
+    {
+      const int B = (s0 + max_pairs <= 2 * npairs) ? max_pairs : 2 * npairs - s0;
+      Sub subs[2];
+      int nsub = 0;
+      for (int d = 0; d < 2; ++d) {
+        const int lo = s0 > d * npairs ? s0 : d * npairs;
+        const int hi = (s0 + B) < (d + 1) * npairs ? (s0 + B) : (d + 1) * npairs;
+        if (hi > lo) subs[nsub++] = Sub{d, lo - d * npairs, hi - lo, lo - s0};
+      }
       const size_t m2 = e.arena.mark();
-      const int f1 = dir == 0 ? b0 : b0 + 1;  // first frame playing image1
-      const int f2 = dir == 0 ? b0 + 1 : b0;  // first frame playing image2
       const long long M = (long long)B * P;
       __half* corr[4];
       for (int l = 0; l < 4; ++l) PP_TRY(pp_alloc(e, &corr[l], (size_t)M * lvl_h[l] * lvl_w[l], "corr level"));
       // all-pairs correlation: grouped GEMM, one group per frame pair, scaled by 1/sqrt(256)
-      {
+      PP_REQUIRE((long long)P * P < (1LL << 31), "raft: frame too large for the correlation volume indexing");
+      for (int si = 0; si < nsub; ++si) {
+        const Sub& sb = subs[si];
+        const int f1 = sb.dir == 0 ? sb.b0 : sb.b0 + 1;  // first frame playing image1
+        const int f2 = sb.dir == 0 ? sb.b0 + 1 : sb.b0;  // first frame playing image2
+        const long long Ms = (long long)sb.cnt * P;
         PPConvParams p;
         memset(&p, 0, sizeof(p));
         p.nseg = 1;
@@ -165,18 +180,14 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
         p.N = 1; p.H = 1; p.W = P; p.OH = 1; p.OW = P; p.Cin = 256;
         p.kh = p.kw = 1; p.sh = p.sw = 1; p.dh = p.dw = 1;
         p.wpacked = fpack + (size_t)f2 * P_pad * 256; p.bias = nullptr;
-        p.Cout_g = P; p.Cout_g_pad = P_pad; p.BN = bn_corr; p.groups = B;
+        p.Cout_g = P; p.Cout_g_pad = P_pad; p.BN = bn_corr; p.groups = sb.cnt;
         p.epi = PP_EPI_STD; p.scale = 1.f / 16.f;
-        p.out = corr[0]; p.out_cstride = P; p.out_coff = 0; p.out_gstep = 0; p.out_fp32 = 0;
-        // group g writes rows [g*P, (g+1)*P): fold the group offset into the row index via out_gstep
-        p.out_gstep = 0;
-        // rows of group g start at g*P*P elements
-        // (out index = m*out_cstride + out_coff + g*out_gstep + n)
-        // P*P may exceed int range only beyond 46340 pixels at 1/8 res (3.7 MPixel frames)
-        PP_REQUIRE((long long)P * P < (1LL << 31), "raft: frame too large for the correlation volume indexing");
+        // group g writes rows [g*P, (g+1)*P) of this sub-range: out index = m*out_cstride + out_coff + g*out_gstep + n
+        // (P*P exceeds the int range only beyond 46340 pixels at 1/8 res, i.e. 3.7 MPixel frames)
+        p.out = corr[0] + (size_t)sb.off * P * P; p.out_cstride = P; p.out_coff = 0; p.out_fp32 = 0;
         p.out_gstep = P * P;
         {
-          PPProfScope ps(e, "conv:raft.corr", (double)M, 2.0 * M * P * 256, (double)M * P * 2 + 2.0 * M * 256 * 2, st);
+          PPProfScope ps(e, "conv:raft.corr", (double)Ms, 2.0 * Ms * P * 256, (double)Ms * P * 2 + 2.0 * Ms * 256 * 2, st);
           PP_TRY(pp_launch_conv(p, st));
         }
         e.launches++;
@@ -201,9 +212,14 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
       PP_TRY(pp_alloc(e, &delta, (size_t)M * 2, "delta"));
       float* ztap;
       PP_TRY(pp_alloc(e, &ztap, (size_t)M * 32, "flow head tap products"));
-      PP_TRY(pp_k_cnet_split(cmap + (size_t)f1 * P * 256, hx, 384, M, st));
+      for (int si = 0; si < nsub; ++si) {
+        const int f1 = subs[si].dir == 0 ? subs[si].b0 : subs[si].b0 + 1;
+        PP_TRY(pp_k_cnet_split(cmap + (size_t)f1 * P * 256, hx + (size_t)subs[si].off * P * 384, 384,
+                               (long long)subs[si].cnt * P, st));
+        e.launches++;
+      }
       PP_TRY(pp_k_raft_coords_init(coords1, flow8, hx, 384, 382, B, h8, w8, st));
-      e.launches += 2;
+      e.launches++;
 
       for (int it = 0; it < iters; ++it) {
         {
@@ -246,9 +262,12 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
                    .act(PP_ACT_RELU).run(st));
         PP_TRY(PPConvCall(e, "raft.update.mask2", B, h8, w8).in(fh, 256, 0, 256).geom(1, 1, 0, 0)
                    .out(mk, 576, 0).act(PP_ACT_NONE, 0.f, 0.25f).run(st));
-        float* dst = (dir == 0 ? flows_f : flows_b) + (size_t)b0 * 2 * H * W;
-        PP_TRY(pp_k_convex_upsample(coords1, mk, dst, B, h8, w8, st));
-        e.launches++;
+        for (int si = 0; si < nsub; ++si) {
+          const Sub& sb = subs[si];
+          float* dst = (sb.dir == 0 ? flows_f : flows_b) + (size_t)sb.b0 * 2 * H * W;
+          PP_TRY(pp_k_convex_upsample(coords1 + (size_t)sb.off * P * 2, mk + (size_t)sb.off * P * 576, dst, sb.cnt, h8, w8, st));
+          e.launches++;
+        }
       }
       e.arena.release(m2);
     }
