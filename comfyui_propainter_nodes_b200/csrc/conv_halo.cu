@@ -29,7 +29,7 @@ namespace {
 constexpr int NUM_THREADS = 352;
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int WARP_A = 8, WARP_B = 9, WARP_MMA = 10;
-constexpr int MAX_SA = 4, MAX_SB = 16;
+constexpr int MAX_SA = 4, MAX_SB = 8;
 constexpr int SMEM_BUDGET = 208 * 1024;
 
 struct HaloParams {
@@ -381,7 +381,7 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
   PP_REQUIRE(enc != nullptr, "conv_halo: cuTensorMapEncodeTiled is not available");
   for (int i = 0; i < p.nseg; ++i) {
     const PPConvSeg& s = p.seg[i];
-    const cuuint64_t cacc = (cuuint64_t)(p.groups - 1) * s.gstep + (s.cend - s.cbegin);
+    const cuuint64_t cacc = (cuuint64_t)(p.groups - 1) * s.gstep + (s.cvalid > 0 ? s.cvalid : s.cend - s.cbegin);
     cuuint64_t dims[4] = {cacc, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
     cuuint64_t strides[3] = {(cuuint64_t)s.cstride * 2, (cuuint64_t)p.W * s.cstride * 2, (cuuint64_t)p.H * p.W * s.cstride * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)h.BW, (cuuint32_t)h.BH, 1};

@@ -273,7 +273,10 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
                   al32(p.out2, p.out2_cstride, p.out2_coff, 0) && (p.epi != PP_EPI_GRU_ZR || ((p.Cout_g >> 1) % 16 == 0)))
                      ? 1 : 0;
   }
-  if (pp_conv_halo_eligible(p)) return pp_launch_conv_halo(p, stream);   // stride-1 k>1 layers: TMA halo-tile kernel
+  if (pp_conv_halo_eligible(p)) return pp_launch_conv_halo(p, stream);
+  for (int i = 0; i < p.nseg; ++i)
+    PP_REQUIRE(p.seg[i].cvalid == 0, "conv: zero-extended input channels (cvalid=%d of %d) need the TMA halo kernel "
+               "(stride 1, zero padding, Cin %% 64 == 0)", p.seg[i].cvalid, p.seg[i].cend - p.seg[i].cbegin);   // stride-1 k>1 layers: TMA halo-tile kernel
   const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
   int stages = SMEM_BUDGET / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;

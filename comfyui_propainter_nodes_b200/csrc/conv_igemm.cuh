@@ -25,6 +25,8 @@ struct PPConvSeg {
   int gstep;     // added to coff per group index
   int cbegin;    // first conv-input channel (per group) covered by this segment
   int cend;      // one past the last conv-input channel covered (multiple of 8)
+  int cvalid;    // 0, or the number of channels that really exist in memory (< cend - cbegin): the rest read as
+                 // zero (TMA out-of-bounds fill; halo kernel only) -- lets a 32-channel tensor feed 64-wide K chunks
 };
 
 struct PPConvParams {

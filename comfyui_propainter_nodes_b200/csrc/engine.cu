@@ -86,6 +86,12 @@ PPConvCall& PPConvCall::gru_h(const __half* h, int h_cs, int h_co, const __half*
 
 int PPConvCall::run(cudaStream_t st) {
   if (err != PP_OK) return err;
+  if (p.nseg == 1 && p.seg[0].cend < p.Cin && p.Cin % 64 == 0 && p.seg[0].gstep == 0) {
+    // weights registered with their input channels zero-padded to a 64 multiple (engine.py PAD64_CONVS): the
+    // tensor only holds the first `cvalid` channels, the TMA loads of the halo kernel zero-fill the rest
+    p.seg[0].cvalid = p.seg[0].cend;
+    p.seg[0].cend = p.Cin;
+  }
   PP_REQUIRE(p.nseg > 0 && p.seg[p.nseg - 1].cend == p.Cin,
              "conv: input segments cover %d channels, weights expect %d", p.nseg ? p.seg[p.nseg - 1].cend : 0, p.Cin);
   PP_REQUIRE(p.out != nullptr, "conv: no output set");
@@ -100,12 +106,9 @@ int PPConvCall::run(cudaStream_t st) {
 int pp_small_conv(PPEngine& e, const std::string& name, const __half* x, int x_cs, int x_co, int C, int cout, void* z,
                   int z_fp32, void* out, int out_cs, int out_co, int out_fp32, int act_tanh, int N, int H, int W,
                   cudaStream_t st) {
-  const void* b;
-  PP_TRY(pp_get_tensor(e, name + ".b", &b));
-  PP_TRY(PPConvCall(e, name + ".taps", N, H, W).in(x, x_cs, x_co, C).geom(1, 1, 0, 0).out(z, 32, 0, z_fp32).run(st));
-  e.launches++;
-  const double rows = (double)N * H * W;
-  PPProfScope ps(e, "tap_sum:" + name, rows, 0.0, rows * (9 * cout * (z_fp32 ? 4 : 2) + cout * (out_fp32 ? 4 : 2)), st);
-  return pp_k_tap_sum3x3(z, z_fp32, 32, static_cast<const float*>(b), cout, out, out_cs, out_co, out_fp32, act_tanh, N, H, W,
-                         st);
+  // 3x3 convs with 2-3 output channels run on the TMA halo-tile kernel with a 16-column N tile: the input patch is
+  // read once (no im2col amplification), so they are bound by streaming the input, not by the taps.
+  (void)cout; (void)z; (void)z_fp32;
+  return PPConvCall(e, name, N, H, W).in(x, x_cs, x_co, C).out(out, out_cs, out_co, out_fp32)
+      .act(act_tanh ? PP_ACT_TANH : PP_ACT_NONE).run(st);
 }

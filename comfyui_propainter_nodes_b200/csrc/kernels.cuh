@@ -75,6 +75,4 @@ int pp_k_prepare_masks(const float* mask, int Tm, int T, int H, int W, int iters
                        float* flow_masks, float* masks_dilated, cudaStream_t st);
 int pp_k_u8_to_unit_float(const uint8_t* src, float* dst, long long n, cudaStream_t st);
 
-// ---- 3x3 conv with <= 3 output channels: 1x1 GEMM (conv_igemm) + this tap gather (conv_small.cu) ----------
-int pp_k_tap_sum3x3(const void* z, int z_fp32, int z_cs, const float* bias, int cout, void* out, int out_cs, int out_co,
-                    int out_fp32, int act_tanh, int N, int H, int W, cudaStream_t st);
+

@@ -29,31 +29,27 @@ __global__ void nhwc_f16_to_nchw_f32(const __half* __restrict__ src, int src_cs,
 }
 
 // Bilinear x2 upsample, align_corners=True (reference deconv: F.interpolate(scale_factor=2, 'bilinear', True)).
-// One thread per (output pixel, 8-channel vector).
-__global__ void upsample2x_ac(const __half* __restrict__ src, int src_cs, int src_co, __half* __restrict__ dst,
-                              int dst_cs, int dst_co, int N, int H, int W, int C8) {
-  const long long total = (long long)N * 2 * H * 2 * W * C8;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = idx % C8;
-  long long p = idx / C8;
+// One thread per (output pixel, 8-channel vector); grid = (x chunks, output rows, images) so all index math is
+// 32-bit and the row interpolation is uniform per block.
+__global__ void __launch_bounds__(256) upsample2x_ac(const __half* __restrict__ src, int src_cs, int src_co,
+                                                     __half* __restrict__ dst, int dst_cs, int dst_co, int H, int W, int C8) {
   const int OW = 2 * W, OH = 2 * H;
-  const int ox = p % OW;
-  p /= OW;
-  const int oy = p % OH;
-  const int n = p / OH;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(OW * C8)) return;
+  const int c8 = idx % (unsigned)C8, ox = idx / (unsigned)C8;
+  const int oy = blockIdx.y, n = blockIdx.z;
   const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
   const float sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
   const float fy = sy * oy, fx = sx * ox;
-  int y0 = (int)fy, x0 = (int)fx;
+  const int y0 = (int)fy, x0 = (int)fx;
   const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
   const float ly = fy - y0, lx = fx - x0;
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
   const __half* base = src + (long long)n * H * W * src_cs + src_co + c8 * 8;
-  const uint4 a = *reinterpret_cast<const uint4*>(base + ((long long)y0 * W + x0) * src_cs);
-  const uint4 b = *reinterpret_cast<const uint4*>(base + ((long long)y0 * W + x1) * src_cs);
-  const uint4 c = *reinterpret_cast<const uint4*>(base + ((long long)y1 * W + x0) * src_cs);
-  const uint4 d = *reinterpret_cast<const uint4*>(base + ((long long)y1 * W + x1) * src_cs);
+  const uint4 a = *reinterpret_cast<const uint4*>(base + (long long)(y0 * W + x0) * src_cs);
+  const uint4 b = *reinterpret_cast<const uint4*>(base + (long long)(y0 * W + x1) * src_cs);
+  const uint4 c = *reinterpret_cast<const uint4*>(base + (long long)(y1 * W + x0) * src_cs);
+  const uint4 d = *reinterpret_cast<const uint4*>(base + (long long)(y1 * W + x1) * src_cs);
   const __half2* ah = reinterpret_cast<const __half2*>(&a);
   const __half2* bh = reinterpret_cast<const __half2*>(&b);
   const __half2* ch = reinterpret_cast<const __half2*>(&c);
@@ -119,9 +115,10 @@ int pp_k_upsample2x(const __half* src, int src_cs, int src_co, __half* dst, int 
                     int W, int C, cudaStream_t st) {
   PP_REQUIRE(C % 8 == 0 && src_cs % 8 == 0 && dst_cs % 8 == 0 && src_co % 8 == 0 && dst_co % 8 == 0,
              "upsample2x: channels must be multiples of 8");
-  const long long total = (long long)N * 4 * H * W * (C / 8);
-  if (total == 0) return PP_OK;
-  upsample2x_ac<<<nblocks(total), TPB, 0, st>>>(src, src_cs, src_co, dst, dst_cs, dst_co, N, H, W, C / 8);
+  if ((long long)N * H * W == 0) return PP_OK;
+  PP_REQUIRE(2 * H <= 65535 && N <= 65535, "upsample2x: %d rows / %d images exceed the grid limits", 2 * H, N);
+  const dim3 grid(pp_ceil_div(2 * W * (C / 8), 256), 2 * H, N);
+  upsample2x_ac<<<grid, 256, 0, st>>>(src, src_cs, src_co, dst, dst_cs, dst_co, H, W, C / 8);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

@@ -187,16 +187,15 @@ __global__ void dcn_sample(const __half* __restrict__ x0, int x0_cs, int x0_co, 
                            const __half* __restrict__ x1, int x1_cs, int x1_co,
                            const __half* __restrict__ offs, int offs_cs, const __half* __restrict__ flow, int flow_cs,
                            int flow_co, float max_mag, __half* __restrict__ cols, int C, int N, int H, int W) {
-  const long long total = (long long)N * H * W * 144;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int gk = idx % 144;           // g*9 + k  (g-major like the offset channels)
-  const long long m = idx / 144;
+  // grid = (chunks of one image's H*W*144 (pixel, group, tap) items, images): 32-bit index math
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(H * W * 144)) return;
+  const int gk = idx % 144u;           // g*9 + k  (g-major like the offset channels)
+  const int pix = idx / 144u;
   const int g = gk / 9, k = gk - g * 9;
-  const int x = m % W;
-  const long long t = m / W;
-  const int y = t % H;
-  const int n = t / H;
+  const int x = pix % (unsigned)W, y = pix / (unsigned)W;
+  const int n = blockIdx.y;
+  const long long m = (long long)n * H * W + pix;
   const __half* o = offs + m * offs_cs;
   float dy = max_mag * tanhf(__half2float(o[2 * gk]));
   float dx = max_mag * tanhf(__half2float(o[2 * gk + 1]));
@@ -402,13 +401,15 @@ int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half
   const int C = C0 + C1;
   PP_REQUIRE(C == 128 || C == 256, "dcn_sample: C=%d must be 128 or 256 (16 offset groups)", C);
   PP_REQUIRE(C0 % 16 == 0, "dcn_sample: C0=%d", C0);
-  const long long total = (long long)N * H * W * 144;
+  if ((long long)N * H * W == 0) return PP_OK;
+  PP_REQUIRE(N <= 65535 && (long long)H * W * 144 < (1LL << 31), "dcn_sample: %d images of %dx%d exceed the grid limits", N, W, H);
+  const dim3 grid(pp_ceil_div(H * W * 144, TPB), N);
   if (C == 128)
-    dcn_sample<8><<<nblocks(total), TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow, flow_cs,
-                                                  flow_co, max_mag, cols, C, N, H, W);
+    dcn_sample<8><<<grid, TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow, flow_cs,
+                                        flow_co, max_mag, cols, C, N, H, W);
   else
-    dcn_sample<16><<<nblocks(total), TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow,
-                                                   flow_cs, flow_co, max_mag, cols, C, N, H, W);
+    dcn_sample<16><<<grid, TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow,
+                                         flow_cs, flow_co, max_mag, cols, C, N, H, W);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

@@ -62,24 +62,38 @@ __global__ void layernorm512(const __half* __restrict__ x, const float* __restri
 
 // Learned depthwise 4x4 stride-4 pooling of the (padded, normalised) tokens (pool_layer,
 // sparse_transformer.py:176-180, 294-297).  x [t][nh][nw][C] -> out [t][ph][pw][C]; w [C][16] fp32.
-__global__ void pool_tokens(const __half* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                            __half* __restrict__ out, int t, int nh, int nw, int ph, int pw, int C) {
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)t * ph * pw * C) return;
-  const int c = idx % C;
-  long long r = idx / C;
-  const int px = r % pw;
-  r /= pw;
-  const int py = r % ph;
-  const int f = r / ph;
-  float acc = b[c];
+__global__ void __launch_bounds__(256) pool_tokens(const __half* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ b, __half* __restrict__ out, int nh, int nw,
+                                                   int ph, int pw, int C) {
+  // one thread per (pooled token, 8-channel vector); w is [16 taps][C] (transposed when registered, engine.py)
+  const int C8 = C >> 3;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(ph * pw * C8)) return;
+  const int c8 = idx % (unsigned)C8;
+  const int r = idx / (unsigned)C8;
+  const int px = r % pw, py = r / pw, f = blockIdx.y;
+  float acc[8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + c8 * 8) + 1);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+  const __half* xb = x + (((long long)f * nh + 4 * py) * nw + 4 * px) * C + c8 * 8;
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 4; ++kx)
-      acc += w[c * 16 + ky * 4 + kx] *
-             __half2float(x[(((long long)f * nh + 4 * py + ky) * nw + 4 * px + kx) * C + c]);
-  out[idx] = __float2half_rn(acc);
+    for (int kx = 0; kx < 4; ++kx) {
+      const uint4 q = *reinterpret_cast<const uint4*>(xb + (long long)(ky * nw + kx) * C);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (ky * 4 + kx) * C + c8 * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (ky * 4 + kx) * C + c8 * 8) + 1);
+      const __half2* hq = reinterpret_cast<const __half2*>(&q);
+      const float2 v0 = __half22float2(hq[0]), v1 = __half22float2(hq[1]), v2 = __half22float2(hq[2]), v3 = __half22float2(hq[3]);
+      acc[0] += w0.x * v0.x; acc[1] += w0.y * v0.y; acc[2] += w0.z * v1.x; acc[3] += w0.w * v1.y;
+      acc[4] += w1.x * v2.x; acc[5] += w1.y * v2.y; acc[6] += w1.z * v3.x; acc[7] += w1.w * v3.y;
+    }
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o[e] = __floats2half2_rn(acc[2 * e], acc[2 * e + 1]);
+  *reinterpret_cast<uint4*>(out + (((long long)f * ph + py) * pw + px) * C + c8 * 8) = *reinterpret_cast<uint4*>(o);
 }
 
 // Window dispatch flags (propainter.py:417-428 max_pool(7,3,3) of the 1/4-res local masks, then
@@ -120,14 +134,11 @@ __global__ void window_flags(const __half* __restrict__ mask4, int cs, int co, c
 __global__ void fold7x7s3(const __half* __restrict__ x, int cs, __half* __restrict__ out, int t, int H, int W, int C,
                           int gh, int gw, int normalise, int gelu) {
   const int C8 = C / 8;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= (long long)t * H * W * C8) return;
-  const int c8 = idx % C8;
-  long long p = idx / C8;
-  const int px = p % W;
-  p /= W;
-  const int py = p % H;
-  const int f = p / H;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;   // grid = (x chunks, rows, frames): 32-bit index math
+  if (idx >= (unsigned)(W * C8)) return;
+  const int c8 = idx % (unsigned)C8, px = idx / (unsigned)C8;
+  const int py = blockIdx.y, f = blockIdx.z;
+  (void)t;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -202,9 +213,9 @@ int pp_k_layernorm(const __half* x, const float* gamma, const float* beta, __hal
 
 int pp_k_pool_tokens(const __half* x, const float* w, const float* b, __half* out, int t, int nh, int nw, int ph,
                      int pw, int C, cudaStream_t st) {
-  const long long total = (long long)t * ph * pw * C;
-  if (total == 0) return PP_OK;
-  pool_tokens<<<nblocks(total), TPB, 0, st>>>(x, w, b, out, t, nh, nw, ph, pw, C);
+  if ((long long)t * ph * pw * C == 0) return PP_OK;
+  PP_REQUIRE(C % 8 == 0 && t <= 65535, "pool_tokens: C=%d t=%d", C, t);
+  pool_tokens<<<dim3(pp_ceil_div(ph * pw * (C / 8), 256), t), 256, 0, st>>>(x, w, b, out, nh, nw, ph, pw, C);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }
@@ -219,8 +230,9 @@ int pp_k_window_flags(const __half* mask4, int cs, int co, const int* win_f0, co
 int pp_k_fold(const __half* x, int cs, __half* out, int t, int H, int W, int C, int gh, int gw, int normalise,
               int gelu, cudaStream_t st) {
   PP_REQUIRE(C % 8 == 0 && cs % 8 == 0, "fold: C=%d cs=%d must be multiples of 8", C, cs);
-  const long long total = (long long)t * H * W * (C / 8);
-  fold7x7s3<<<nblocks(total), TPB, 0, st>>>(x, cs, out, t, H, W, C, gh, gw, normalise, gelu);
+  if ((long long)t * H * W == 0) return PP_OK;
+  PP_REQUIRE(H <= 65535 && t <= 65535, "fold: %d rows / %d frames exceed the grid limits", H, t);
+  fold7x7s3<<<dim3(pp_ceil_div(W * (C / 8), 256), H, t), 256, 0, st>>>(x, cs, out, t, H, W, C, gh, gw, normalise, gelu);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

@@ -244,7 +244,7 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
         for n in ("norm1", "norm2"):
             tens[o + n + ".weight"] = g[t + n + ".weight"].float()
             tens[o + n + ".bias"] = g[t + n + ".bias"].float()
-        tens[o + "pool.weight"] = g[a + "pool_layer.weight"].reshape(512, 16).float()
+        tens[o + "pool.weight"] = g[a + "pool_layer.weight"].reshape(512, 16).float().t().contiguous()   # [tap][C]
         tens[o + "pool.bias"] = g[a + "pool_layer.bias"].float()
         expect = torch.from_numpy(Wspec.rolled_valid_indices())
         if not torch.equal(g[a + "valid_ind_rolled"].cpu().long(), expect):
@@ -327,22 +327,15 @@ class Engine:
         self._keep.append(t)
         self._check(self.lib.pp_register_tensor(self.h, name.encode(), _ptr(t), t.numel() * 4))
 
-    # 3x3 layers with <= 3 output channels: 1x1 GEMM producing the 9*cout per-tap partial products + tap gather
-    SMALL_CONVS = ("raft.update.fh2", "gen.decoder.6", "rfc.upsample.deconv")
-
-    def register_small_conv(self, name, w, b):
-        """[cout, C, 3, 3] -> 1x1 conv '<name>.taps' with output channel tap*cout + c, bias tensor '<name>.b'."""
-        cout, C = w.shape[0], w.shape[1]
-        wt = w.detach().float().permute(2, 3, 0, 1).reshape(9 * cout, C, 1, 1)   # [(ky,kx,c), ch]
-        self.register_conv(name + ".taps", wt, None)
-        self.register_tensor(name + ".b", b)
+    # Stride-1 k>1 layers with 32 input channels: kernel channels zero-padded to 64 so they run on the TMA halo-tile
+    # kernel (64-channel K chunks); the activation tensors keep 32 channels, TMA zero-fills the rest (PPConvSeg.cvalid)
+    PAD64_CONVS = ("rfc.encoder1.0.conv1", "rfc.encoder1.0.conv2", "rfc.upsample.0", "rfc.upsample.deconv")
 
     def load_weights(self, raft_sd, rfc_sd, gen_sd):
         convs, tens = build_layers(raft_sd, rfc_sd, gen_sd)
         for name, (w, b, groups, cin_map) in convs.items():
-            if name in self.SMALL_CONVS:
-                self.register_small_conv(name, w, b)
-                continue
+            if name in self.PAD64_CONVS and cin_map is None and w.shape[1] < 64:
+                cin_map = _pad_map(w.shape[1], 64)
             self.register_conv(name, w, b, groups, cin_map)
         for name, t in tens.items():
             self.register_tensor(name, t)
