@@ -327,15 +327,16 @@ class Engine:
         self._keep.append(t)
         self._check(self.lib.pp_register_tensor(self.h, name.encode(), _ptr(t), t.numel() * 4))
 
-    # Stride-1 k>1 layers with 32 input channels: kernel channels zero-padded to 64 so they run on the TMA halo-tile
+    # Stride-1 k>1 layers with 32 / 96 input channels: kernel channels zero-padded to a multiple of 64 so they run on the TMA halo-tile
     # kernel (64-channel K chunks); the activation tensors keep 32 channels, TMA zero-fills the rest (PPConvSeg.cvalid)
-    PAD64_CONVS = ("rfc.encoder1.0.conv1", "rfc.encoder1.0.conv2", "rfc.upsample.0", "rfc.upsample.deconv")
+    PAD64_CONVS = ("rfc.encoder1.0.conv1", "rfc.encoder1.0.conv2", "rfc.upsample.0", "rfc.upsample.deconv") + tuple(
+        f"raft.{net}.layer2.{blk}" for net in ("fnet", "cnet") for blk in ("0.conv2", "1.conv1", "1.conv2"))   # 96 ch
 
     def load_weights(self, raft_sd, rfc_sd, gen_sd):
         convs, tens = build_layers(raft_sd, rfc_sd, gen_sd)
         for name, (w, b, groups, cin_map) in convs.items():
-            if name in self.PAD64_CONVS and cin_map is None and w.shape[1] < 64:
-                cin_map = _pad_map(w.shape[1], 64)
+            if name in self.PAD64_CONVS and cin_map is None and w.shape[1] % 64 != 0:
+                cin_map = _pad_map(w.shape[1], (w.shape[1] + 63) // 64 * 64)
             self.register_conv(name, w, b, groups, cin_map)
         for name, t in tens.items():
             self.register_tensor(name, t)
