@@ -253,7 +253,7 @@ def run_b200(args, rank, world):
         conv_fl = sum(v["flops"] for v in conv.values())
         all_ms = sum(v["ms"] for v in prof.values())
         ach = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all conv/linear layers)",
+        roof = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_igemm_kernel (tcgen05 convolutions: TMA halo-tile kernel for stride-1 convs and linears, cp.async implicit GEMM for the rest), aggregate over all conv launches of the step",
                 "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
                 "traffic": None, "peak_source": pk["source"] + " bf16 sustained", "share_of_profiled_step": conv_ms / all_ms if all_ms else None,
                 "launches": sum(v["count"] for v in conv.values())}
@@ -265,7 +265,7 @@ def run_b200(args, rank, world):
                               "frac": gbs / pk["hbm"], "launches": v["count"], "ms": v["ms"]})
         if "attention" in prof:
             v = prof["attention"]
-            extra.append({"kernel": "window_attention (mma.sync, flops upper bound: all windows masked)", "bound": "tensor",
+            extra.append({"kernel": "window_attention_tc (tcgen05) + window_attention (mma.sync, unmasked windows); flops are an upper bound (all windows masked)", "bound": "tensor",
                           "ms": v["ms"], "launches": v["count"]})
         if args.profile_out:
             with open(args.profile_out, "w") as fh:

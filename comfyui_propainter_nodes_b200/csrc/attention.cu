@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(NT) window_attention(const AttnParams p) {
 int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs, const __half* pk, const __half* pv,
                    int pool_cs, __half* out, int out_cs, const int* win_flags, const int* ring_idx,
                    const int* sw_frame_off, const int* sw_t, int n_sliding, int t_max, int gh, int gw, int nh, int nw,
-                   int n_pool, int t_parity, cudaStream_t st) {
+                   int n_pool, int t_parity, int* key_tab, int key_tab_stride, cudaStream_t st) {
   PP_REQUIRE(nh % 5 == 0 && nw % 9 == 0, "attention: padded grid %dx%d is not a multiple of the 5x9 window", nh, nw);
   AttnParams p;
   p.q = q; p.k = k; p.v = v; p.qkv_cs = qkv_cs; p.pk = pk; p.pv = pv; p.pool_cs = pool_cs;
@@ -233,6 +233,7 @@ int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs
   p.n_win = (nh / 5) * (nw / 9);
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   p.only_unmasked = 1;
+  p.key_tab = key_tab; p.key_tab_stride = key_tab_stride;
   PP_TRY(pp_launch_attention_tc(p, n_sliding, t_max, st));   // masked windows: tcgen05 / TMEM
   dim3 grid(t_max, p.n_win * 4, n_sliding);                  // unmasked windows: one 45x45 problem per frame
   const size_t smem = (size_t)(BQ + 4 * BKEY) * 256;

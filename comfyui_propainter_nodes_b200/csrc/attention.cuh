@@ -13,6 +13,7 @@ struct PPAttnParams {
   const int* sw_t;                                                // [n_sliding] frames in each sliding window
   int n_win, gh, gw, nh, nw, nww, n_pool, parity;
   int only_unmasked;                                              // mma.sync kernel: skip masked windows
+  const int* key_tab; int key_tab_stride;                         // [n_win][stride] gather table scratch (attention_tc.cu)
   float scale_log2;
 };
 

@@ -32,6 +32,24 @@ __device__ __forceinline__ uint32_t tile_off(uint32_t panel, int row, int chunk)
   return (uint32_t)(chunk >> 3) * panel + (uint32_t)row * 128 + (uint32_t)(((chunk & 7) ^ (row & 7)) << 4);
 }
 
+// Key-row gather table: entry j of window `win` is the source row of key j of a masked window, as an offset (in
+// 16-byte units, relative to the first frame of the sliding window) into the K/V token tensor, or -- top bit set --
+// into the pooled K/V tensor.  Keys of T_ind frame fi (frame parity + 2*fi) are [own 45 | ring 148 | pooled n_pool].
+// Built once per launch so that the gather loop of the attention kernel does no integer division or index math.
+__global__ void attn_key_table(int* __restrict__ tab, const int* __restrict__ ring_idx, int nk_max, int kpf, int ntok,
+                               int n_pool, int qkv_cs, int pool_cs, int parity) {
+  const int win = blockIdx.x;
+  const int* ring = ring_idx + win * RING;
+  for (int j = threadIdx.x; j < nk_max; j += blockDim.x) {
+    const int fi = j / kpf, w = j - fi * kpf;
+    const int fr = parity + 2 * fi;
+    unsigned e;
+    if (w < RING) e = (unsigned)(((long long)fr * ntok + ring[w]) * qkv_cs / 8);
+    else e = 0x80000000u | (unsigned)(((long long)fr * n_pool + (w - RING)) * pool_cs / 8);
+    tab[(long long)win * nk_max + j] = (int)e;
+  }
+}
+
 __global__ void __launch_bounds__(NT, 2) window_attention_tc(const PPAttnParams p) {
   using namespace ppx;
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
@@ -75,26 +93,32 @@ __global__ void __launch_bounds__(NT, 2) window_attention_tc(const PPAttnParams 
     const __half* src = p.q + ((long long)fr * ntok + ring[pos]) * p.qkv_cs + head * D + ch * 8;
     cp_async16(sbase + SM_Q + tile_off(QPANEL, r, ch), src, 16);
   }
+  // K/V gather: thread owns 16-byte chunk `ch` of rows r0, r0+16, r0+32, r0+48 of every key tile; the source row of
+  // key j comes from the per-window table (attn_key_table), so the loop body is a table load, two adds and two copies
+  const int r0 = tid >> 4, ch = tid & 15;
+  const long long fb = frame_base;
+  const __half* kb = p.k + fb * ntok * p.qkv_cs + head * D + ch * 8;
+  const __half* vb = p.v + fb * ntok * p.qkv_cs + head * D + ch * 8;
+  const __half* pkb = p.pk + fb * p.n_pool * p.pool_cs + head * D + ch * 8;
+  const __half* pvb = p.pv + fb * p.n_pool * p.pool_cs + head * D + ch * 8;
+  const int* ktab = p.key_tab + (long long)win * p.key_tab_stride;
+  const uint32_t kv_dst0 = sbase + tile_off(KPANEL, r0, ch);
   auto load_kv = [&](int tile, int stage) {
-    for (int i = tid; i < BKEY * 16; i += NT) {
-      const int r = i >> 4, ch = i & 15;
-      const int j = tile * BKEY + r;
-      const __half* ks = p.k; const __half* vs = p.v;
+    const uint32_t dk = kv_dst0 + SM_K + stage * KTILE, dv = kv_dst0 + SM_V + stage * KTILE;
+#pragma unroll
+    for (int it = 0; it < BKEY / 16; ++it) {
+      const int j = tile * BKEY + r0 + 16 * it;
+      const __half* ks = kb; const __half* vs = vb;
       uint32_t nbytes = 0;
       if (j < nk) {
         nbytes = 16;
-        const int fi = j / kpf, w = j - fi * kpf;
-        const int fr = frame_base + p.parity + 2 * fi;
-        if (w < RING) {
-          const long long off = ((long long)fr * ntok + ring[w]) * p.qkv_cs + head * D + ch * 8;
-          ks = p.k + off; vs = p.v + off;
-        } else {
-          const long long off = ((long long)fr * p.n_pool + (w - RING)) * p.pool_cs + head * D + ch * 8;
-          ks = p.pk + off; vs = p.pv + off;
-        }
+        const int e = __ldg(ktab + j);
+        const long long off = (long long)(e & 0x7fffffff) * 8;
+        ks = (e < 0 ? pkb : kb) + off;
+        vs = (e < 0 ? pvb : vb) + off;
       }
-      cp_async16(sbase + SM_K + stage * KTILE + tile_off(KPANEL, r, ch), ks, nbytes);
-      cp_async16(sbase + SM_V + stage * KTILE + tile_off(KPANEL, r, ch), vs, nbytes);
+      cp_async16(dk + it * 2048, ks, nbytes);     // rows r0 + 16*it: same swizzle phase, 16 rows * 128 B further
+      cp_async16(dv + it * 2048, vs, nbytes);
     }
     cp_async_commit();
   };
@@ -251,6 +275,14 @@ int pp_launch_attention_tc(const PPAttnParams& p, int n_sliding, int t_max, cuda
     PP_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PP_CUDA_CHECK(cudaFuncSetAttribute(window_attention_tc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
+  }
+  {
+    const int kpf = RING + p.n_pool, nk_max = ((t_max - p.parity + 1) / 2) * kpf;
+    PP_REQUIRE(p.key_tab != nullptr && p.key_tab_stride >= nk_max, "attention: key table scratch too small (%d < %d)",
+               p.key_tab_stride, nk_max);
+    attn_key_table<<<p.n_win, 256, 0, st>>>(const_cast<int*>(p.key_tab), p.ring_idx, p.key_tab_stride, kpf, p.nh * p.nw, p.n_pool,
+                                           p.qkv_cs, p.pool_cs, p.parity);
+    PP_CUDA_CHECK(cudaGetLastError());
   }
   dim3 grid(pp_ceil_div(t_max * WIN_TOK, BQ), p.n_win * 4, n_sliding);
   window_attention_tc<<<grid, NT, smem, st>>>(p);

@@ -235,9 +235,12 @@ int pp_op_attention(pp_handle h, const void* qkv_f16, const void* pkv_f16, void*
   int* meta_dev;
   PP_TRY(pp_alloc(e, &meta_dev, 2, "attention meta"));
   PP_CUDA_CHECK(cudaMemcpyAsync(meta_dev, meta_host, sizeof(meta_host), cudaMemcpyHostToDevice, as_stream(stream)));
+  const int key_stride = ((t + 1) / 2) * (193 + n_pool);
+  int* key_tab;
+  PP_TRY(pp_alloc(e, &key_tab, (size_t)(nh / 5) * (nw / 9) * key_stride, "attention key table"));
   int r = pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, static_cast<__half*>(out_f16), 512,
                          win_flags_dev, ring_dev, meta_dev, meta_dev + 1, 1, t, gh, gw, nh, nw, n_pool, parity,
-                         as_stream(stream));
+                         key_tab, key_stride, as_stream(stream));
   PP_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
   e.arena.release(mark);
   e.launches++;

@@ -147,8 +147,9 @@ int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, 
                .out(b10, 512, 0, 0, 256).act(PP_ACT_LRELU, s).run(st));
     PP_TRY(PPConvCall(e, "gen.encoder.12", n, h4, w4).in(x0, 256, 0, 64, 64).in(b10, 512, 0, 128, 128)
                .out(b12, 384, 0, 0, 96).act(PP_ACT_LRELU, s).run(st));
-    PP_TRY(PPConvCall(e, "gen.encoder.14", n, h4, w4).in(x0, 256, 0, 32, 32).in(b12, 384, 0, 48, 48)
-               .out(b14, 256, 0, 0, 32).act(PP_ACT_LRELU, s).run(st));
+    // 8 groups of 80 -> 32 channels: dense block-diagonal weights (engine.py), one launch on the halo kernel
+    PP_TRY(PPConvCall(e, "gen.encoder.14", n, h4, w4).in(x0, 256, 0, 256).in(b12, 384, 0, 384)
+               .out(b14, 256, 0).act(PP_ACT_LRELU, s).run(st));
     PP_TRY(PPConvCall(e, "gen.encoder.16", n, h4, w4).in(x0, 256, 0, 256).in(b14, 256, 0, 256)
                .out(g.enc + (size_t)f0 * P4 * 128, 128, 0).act(PP_ACT_LRELU, s).run(st));
   }
@@ -339,6 +340,11 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
                            flags, st));
   e.launches++;
 
+  // gather table scratch of the tcgen05 attention kernel: [5x9 windows][keys of a masked window]
+  const int key_stride = ((t_max + 1) / 2) * (193 + np);
+  int* key_tab;
+  PP_TRY(pp_alloc(e, &key_tab, (size_t)(nh / WIN_H) * (nw / WIN_W) * key_stride, "attention key table"));
+
   for (int blk = 0; blk < 8; ++blk) {
     const std::string b = "gen.tf." + std::to_string(blk) + ".";
     const void *g1, *b1, *g2, *b2, *pwt, *pbs;
@@ -359,7 +365,8 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
         fl += 4.0 * win_t[w] * nh * nw * ((win_t[w] - blk % 2 + 1) / 2) * (193 + np) * 512;
       PPProfScope ps(e, "attention", (double)rows_pad, fl, 0.0, st);
       PP_TRY(pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, att, 512, flags, g.ring_idx,
-                            tab_dev + o_foff, tab_dev + o_t, n_sw, t_max, gh, gw, nh, nw, np, blk % 2, st));
+                            tab_dev + o_foff, tab_dev + o_t, n_sw, t_max, gh, gw, nh, nw, np, blk % 2, key_tab, key_stride,
+                            st));
     }
     PP_TRY(PPConvCall(e, b + "proj", 1, 1, (int)rows).in(att, 512, 0, 512).out(x, 512, 0).residual(x, 512, 0).run(st));
     PP_TRY(pp_k_layernorm(x, (const float*)g2, (const float*)b2, y, rows, gh, gw, gh, gw, st));

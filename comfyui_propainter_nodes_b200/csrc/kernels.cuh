@@ -65,7 +65,7 @@ int pp_k_fold(const __half* x, int cs, __half* out, int t, int H, int W, int C, 
 int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs, const __half* pk, const __half* pv,
                    int pool_cs, __half* out, int out_cs, const int* win_flags, const int* ring_idx,
                    const int* sw_frame_off, const int* sw_t, int n_sliding, int t_max, int gh, int gw, int nh, int nw,
-                   int n_pool, int t_parity, cudaStream_t st);
+                   int n_pool, int t_parity, int* key_tab, int key_tab_stride, cudaStream_t st);
 int pp_k_composite(const __half* pred, int pred_cs, const float* masks, const uint8_t* orig, uint8_t* comp,
                    const int* frame_ids, const int* first_visit, int lt, int H, int W, cudaStream_t st);
 

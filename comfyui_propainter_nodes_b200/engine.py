@@ -213,8 +213,23 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
     Wspec.check_state_dict(g, Wspec.generator_spec())
     enc_groups = {0: 1, 2: 1, 4: 1, 6: 1, 8: 1, 10: 2, 12: 4, 14: 8, 16: 1}
     for i, gr in enc_groups.items():
-        add(f"gen.encoder.{i}", g[f"encoder.layers.{i}.weight"], g[f"encoder.layers.{i}.bias"], gr,
-            _pad_map(5, 8) if i == 0 else None)
+        w = g[f"encoder.layers.{i}.weight"]
+        if i == 14:
+            # groups of 80 input / 32 output channels are too small for 64-wide K chunks and 128-column tiles: run the
+            # layer dense with block-diagonal weights (8x the MACs, all of them on the TMA halo-tile kernel at >10x the
+            # rate).  Kernel channel order = cat(x0[256], previous output[384]); group k owns x0[32k:32k+32] and
+            # prev[48k:48k+48] (propainter.py:268-273).
+            cout, cg = w.shape[0], w.shape[1]
+            nx, npv = 256 // gr, 384 // gr
+            assert cg == nx + npv and cout % gr == 0
+            dense = torch.zeros(cout, 640, w.shape[2], w.shape[3])
+            for k in range(gr):
+                rows = slice(k * (cout // gr), (k + 1) * (cout // gr))
+                dense[rows, k * nx:(k + 1) * nx] = w[rows, :nx]
+                dense[rows, 256 + k * npv:256 + (k + 1) * npv] = w[rows, nx:]
+            add("gen.encoder.14", dense, g["encoder.layers.14.bias"], 1, None)
+            continue
+        add(f"gen.encoder.{i}", w, g[f"encoder.layers.{i}.bias"], gr, _pad_map(5, 8) if i == 0 else None)
     for dst, src in (("0", "0.conv"), ("2", "2"), ("4", "4.conv"), ("6", "6")):
         add("gen.decoder." + dst, g[f"decoder.{src}.weight"], g[f"decoder.{src}.bias"])
     add("gen.ss", g["ss.embedding.weight"].view(512, 128, 7, 7), g["ss.embedding.bias"])
