@@ -134,16 +134,21 @@ class ProPainterOutpaint:
     def propainter_outpainting(self, image, width, height, width_scale, height_scale, mask_dilates,
                                flow_mask_dilates, ref_stride, neighbor_length, subvideo_length, raft_iter, fp16):
         device = _compute_device()
-        frames = iu.convert_image_to_frames(image)
         n = image.size(dim=0)
-        icfg = iu.ImageOutpaintConfig(width, height, mask_dilates, flow_mask_dilates, frames[0].size, n,
+        input_size = (image.size(dim=2), image.size(dim=1))
+        icfg = iu.ImageOutpaintConfig(width, height, mask_dilates, flow_mask_dilates, input_size, n,
                                       width_scale, height_scale)
         cfg = ProPainterConfig(ref_stride, neighbor_length, subvideo_length, raft_iter, fp16, n, device,
                                icfg.outpaint_size)
-        canvas, flow_masks, masks_dilated = iu.extrapolation(frames, icfg)
-        ft, fm, md, originals = iu.prepare_frames_and_masks_for_outpaint(canvas, flow_masks, masks_dilated, device)
+        if tuple(icfg.process_size) == tuple(input_size):
+            # no resize: canvas and band masks are assembled on the device (same integer semantics)
+            ft, fm, md, orig = iu.outpaint_tensors(image, icfg, device)
+        else:
+            canvas, flow_masks, masks_dilated = iu.extrapolation(iu.convert_image_to_frames(image), icfg)
+            ft, fm, md, originals = iu.prepare_frames_and_masks_for_outpaint(canvas, flow_masks, masks_dilated, device)
+            orig = torch.from_numpy(np.stack(originals))
         models = initialize_models(cfg.device, cfg.fp16)
-        images, out_masks, _ = _run(models, ft, fm, md, torch.from_numpy(np.stack(originals)), cfg)
+        images, out_masks, _ = _run(models, ft, fm, md, orig, cfg)
         out_w, out_h = cfg.process_size
         return images, out_masks, out_w, out_h
 

@@ -139,6 +139,29 @@ def prepare_frames_and_masks_for_outpaint(frames, flow_masks, masks_dilated, dev
     return _tensorise(frames, flow_masks, masks_dilated, device)
 
 
+def outpaint_tensors(images: torch.Tensor, config: ImageOutpaintConfig, device):
+    """Tensor version of convert_image_to_frames + extrapolation + prepare_frames_and_masks_for_outpaint for the
+    no-resize case (process_size == input_size): the same integer semantics (uint8 truncation, zero canvas, side-band
+    masks with the 4-px inset) with a handful of tensor ops on `device` instead of per-frame PIL/numpy work.
+    -> frames [1,T,3,H',W'] in [-1,1], flow_masks / masks_dilated [1,T,1,H',W'] in {0,1}, originals uint8 [T,H',W',3]."""
+    assert tuple(config.process_size) == tuple(config.input_size)
+    T, rh, rw = images.shape[0], images.shape[1], images.shape[2]
+    pw, ph = config.outpaint_size
+    x0, y0 = int((pw - rw) / 2), int((ph - rh) / 2)
+    q = (images.to(device=device, dtype=torch.float32) * 255).clamp_(0, 255).to(torch.uint8)   # truncation
+    canvas = torch.zeros(T, ph, pw, 3, dtype=torch.uint8, device=device)
+    canvas[:, y0:y0 + rh, x0:x0 + rw] = q
+    ih, iw = (4 if y0 > 10 else 0), (4 if x0 > 10 else 0)
+    band = torch.ones(ph, pw, dtype=torch.float32, device=device)
+    band[y0 + ih:y0 + rh - ih, x0 + iw:x0 + rw - iw] = 0
+    flow = band.clone()
+    band[y0:y0 + rh, x0:x0 + rw] = 0
+    ft = canvas.permute(0, 3, 1, 2).to(torch.float32).div_(255).unsqueeze(0) * 2 - 1
+    fm = flow.view(1, 1, 1, ph, pw).expand(1, T, 1, ph, pw).contiguous()
+    md = band.view(1, 1, 1, ph, pw).expand(1, T, 1, ph, pw).contiguous()
+    return ft, fm, md, canvas
+
+
 def handle_output(composed_frames, flow_masks: torch.Tensor, masks_dilated: torch.Tensor):
     """uint8 HWC frames -> IMAGE [T,H,W,3] float32 CPU; masks squeezed to [T,H,W] (reference :276-290)."""
     if isinstance(composed_frames, torch.Tensor):

@@ -151,3 +151,17 @@ def test_outpaint_canvas():
     assert a.shape == (64, 144, 3) and (a[:, :24] == 0).all() and (a[:, 24:120] > 0).any()
     assert (m[:, :24] == 255).all() and (m[:, 24:120] == 0).all()
     assert (f[:, :28] == 255).all() and (f[:, 28:116] == 0).all()   # 4-px inset of the flow mask
+
+
+def test_outpaint_tensor_path_matches_pil_path():
+    """The device-side canvas / band-mask assembly equals the reference-style PIL path bit for bit."""
+    from comfyui_propainter_nodes_b200.utils import image_utils as IU
+    g = torch.Generator().manual_seed(5)
+    for (T, H, W, ws, hs) in ((3, 48, 64, 1.2, 1.0), (2, 40, 56, 1.5, 1.3), (2, 32, 32, 1.0, 1.26)):
+        image = torch.rand(T, H, W, 3, generator=g)
+        cfg = IU.ImageOutpaintConfig(W, H, 5, 8, (W, H), T, ws, hs)
+        canvas, fm_l, md_l = IU.extrapolation(IU.convert_image_to_frames(image), cfg)
+        ft0, fm0, md0, orig0 = IU.prepare_frames_and_masks_for_outpaint(canvas, fm_l, md_l, torch.device("cpu"))
+        ft1, fm1, md1, orig1 = IU.outpaint_tensors(image, cfg, torch.device("cpu"))
+        assert torch.equal(ft0, ft1) and torch.equal(fm0, fm1) and torch.equal(md0, md1)
+        assert np.array_equal(np.stack(orig0), orig1.numpy())
