@@ -86,11 +86,13 @@ PPConvCall& PPConvCall::gru_h(const __half* h, int h_cs, int h_co, const __half*
 
 int PPConvCall::run(cudaStream_t st) {
   if (err != PP_OK) return err;
-  if (p.nseg == 1 && p.seg[0].cend < p.Cin && p.Cin % 64 == 0 && p.seg[0].gstep == 0) {
-    // weights registered with their input channels zero-padded to a 64 multiple (engine.py PAD64_CONVS): the
-    // tensor only holds the first `cvalid` channels, the TMA loads of the halo kernel zero-fill the rest
-    p.seg[0].cvalid = p.seg[0].cend;
-    p.seg[0].cend = p.Cin;
+  if (p.nseg > 0 && p.seg[p.nseg - 1].cend < p.Cin && p.Cin % 64 == 0 && p.Cin - p.seg[p.nseg - 1].cend < 64 &&
+      p.seg[p.nseg - 1].gstep == 0) {
+    // weights registered with their input channels zero-padded to a 64 multiple (engine.py PAD64_CONVS): the last
+    // segment's tensor only holds `cvalid` channels, the TMA loads of the halo kernel zero-fill the rest
+    PPConvSeg& last = p.seg[p.nseg - 1];
+    last.cvalid = last.cend - last.cbegin;
+    last.cend = p.Cin;
   }
   PP_REQUIRE(p.nseg > 0 && p.seg[p.nseg - 1].cend == p.Cin,
              "conv: input segments cover %d channels, weights expect %d", p.nseg ? p.seg[p.nseg - 1].cend : 0, p.Cin);

@@ -55,18 +55,6 @@ int deconv(PPEngine& e, const std::string& name, const __half* x, int n, int h, 
 
 }  // namespace
 
-// 3x3 conv over cat(64-aligned feature segments, 8 mask/flow channels) + LeakyReLU as two launches: the 8-channel
-// tail (+ bias) writes the partial sum into `out`, the main part (TMA halo-tile kernel) adds it as residual before
-// the activation.  Weights "<name>.main" / "<name>.tail" are registered by the packer (engine.py build_layers).
-static int conv_split_tail(PPEngine& e, const std::string& name, int n, int h, int w, const __half* const* seg_ptr,
-                           const int* seg_cs, const int* seg_co, const int* seg_ch, int nseg, const __half* tail,
-                           int tail_cs, int tail_co, __half* out, float slope, cudaStream_t st) {
-  PP_TRY(PPConvCall(e, name + ".tail", n, h, w).in(tail, tail_cs, tail_co, 8).out(out, 128, 0).run(st));
-  PPConvCall c(e, name + ".main", n, h, w);
-  for (int i = 0; i < nseg; ++i) c.in(seg_ptr[i], seg_cs[i], seg_co[i], seg_ch[i]);
-  return c.out(out, 128, 0).residual(out, 128, 0).act(PP_ACT_NONE, slope, 1.f, PP_ACT_LRELU).run(st);
-}
-
 int pp_stage_gen_end(PPEngine& e) {
   if (e.gen.active) {
     e.arena.release(e.gen.arena_mark);
@@ -274,10 +262,7 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
             PP_TRY(pp_k_featprop_cond(cur, 128, pprev, 128, fprop, fchk, m2, 8, cond, 264, n, h4, w4, 128, st));
           }
           e.launches++;
-          {
-            const __half* sp[1] = {cond}; const int scs[1] = {264}, sco[1] = {0}, sch[1] = {256};
-            PP_TRY(conv_split_tail(e, m + ".offset.0", n, h4, w4, sp, scs, sco, sch, 1, cond, 264, 256, o1, 0.1f, st));
-          }
+          PP_TRY(PPConvCall(e, m + ".offset.0", n, h4, w4).in(cond, 264, 0, 264).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
           PP_TRY(PPConvCall(e, m + ".offset.1", n, h4, w4).in(o1, 128, 0, 128).out(o2, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
           PP_TRY(PPConvCall(e, m + ".offset.2", n, h4, w4).in(o2, 128, 0, 128).out(o1, 128, 0).act(PP_ACT_LRELU, 0.1f).run(st));
           PP_TRY(PPConvCall(e, m + ".offset.3", n, h4, w4).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
@@ -292,19 +277,15 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
           prop = aligned;
         }
         // feat_prop = feat_prop + backbone(cat(cur, feat_prop, mask_current))
-        {
-          const __half* sp[2] = {cur, prop}; const int scs[2] = {128, 128}, sco[2] = {0, 0}, sch[2] = {128, 128};
-          PP_TRY(conv_split_tail(e, m + ".backbone.0", n, h4, w4, sp, scs, sco, sch, 2, m2, 8, 0, bb, 0.2f, st));
-        }
+        PP_TRY(PPConvCall(e, m + ".backbone.0", n, h4, w4).in(cur, 128, 0, 128).in(prop, 128, 0, 128).in(m2, 8, 0, 8)
+                   .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
         PP_TRY(PPConvCall(e, m + ".backbone.1", n, h4, w4).in(bb, 128, 0, 128).out(dst + (size_t)idx * slab, 128, 0)
                    .residual(prop, 128, 0).run(st));
       }
     }
     // fuse(cat(out_b, out_f, mask)) + x over every (k, window) frame of the group; result reuses `ob`
-    {
-      const __half* sp[2] = {ob, of}; const int scs[2] = {128, 128}, sco[2] = {0, 0}, sch[2] = {128, 128};
-      PP_TRY(conv_split_tail(e, "gen.fp.fuse.0", L * n, h4, w4, sp, scs, sco, sch, 2, M2, 8, 0, bb, 0.2f, st));
-    }
+    PP_TRY(PPConvCall(e, "gen.fp.fuse.0", L * n, h4, w4).in(ob, 128, 0, 128).in(of, 128, 0, 128).in(M2, 8, 0, 8)
+               .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
     PP_TRY(PPConvCall(e, "gen.fp.fuse.1", L * n, h4, w4).in(bb, 128, 0, 128).out(of, 128, 0).residual(X, 128, 0).run(st));
     // scatter [k][w] -> window-major slots (async D2D copies: n*L small, frame sized)
     for (int k = 0; k < L; ++k)

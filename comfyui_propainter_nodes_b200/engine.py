@@ -264,18 +264,6 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
         expect = torch.from_numpy(Wspec.rolled_valid_indices())
         if not torch.equal(g[a + "valid_ind_rolled"].cpu().long(), expect):
             raise ValueError("checkpoint's valid_ind_rolled differs from the 5x9 window ring this engine implements")
-    # Layers whose input is [k*64 feature channels | a few mask/flow channels] (cat(cur, prop, mask) = 264 kernel
-    # channels): "<name>.main" covers the 64-aligned part (TMA halo-tile kernel, no bias) and "<name>.tail" the rest
-    # (+ bias); the call site runs tail -> partial sum, then main with the partial as residual.  conv(x) is linear in
-    # the channel split, so the sum is the same convolution.
-    for name in [n for n in convs if n.endswith((".offset.0", ".backbone.0", "fuse.0")) and n.startswith("gen.fp.")]:
-        w, b, groups, cmap = convs[name]
-        cmap = cmap if cmap is not None else list(range(w.shape[1]))
-        cut = len(cmap) // 64 * 64
-        if groups != 1 or cut == 0 or cut == len(cmap):
-            continue
-        convs[name + ".main"] = (w, None, 1, cmap[:cut])
-        convs[name + ".tail"] = (w, b, 1, cmap[cut:])
     return convs, tens
 
 
@@ -342,16 +330,21 @@ class Engine:
         self._keep.append(t)
         self._check(self.lib.pp_register_tensor(self.h, name.encode(), _ptr(t), t.numel() * 4))
 
-    # Stride-1 k>1 layers with 32 / 96 input channels: kernel channels zero-padded to a multiple of 64 so they run on the TMA halo-tile
-    # kernel (64-channel K chunks); the activation tensors keep 32 channels, TMA zero-fills the rest (PPConvSeg.cvalid)
+    # Stride-1 k>1 layers whose input channels are not a multiple of 64: kernel channels zero-padded to the next
+    # multiple so they run on the TMA halo-tile kernel (64-channel K chunks); the activation tensors keep their real
+    # channel count, TMA zero-fills the rest of the last segment (PPConvSeg.cvalid)
     PAD64_CONVS = ("rfc.encoder1.0.conv1", "rfc.encoder1.0.conv2", "rfc.upsample.0", "rfc.upsample.deconv") + tuple(
-        f"raft.{net}.layer2.{blk}" for net in ("fnet", "cnet") for blk in ("0.conv2", "1.conv1", "1.conv2"))   # 96 ch
+        f"raft.{net}.layer2.{blk}" for net in ("fnet", "cnet") for blk in ("0.conv2", "1.conv1", "1.conv2")) + (  # 96 ch
+        # cat(features[256], mask/flow[8]) = 264 kernel channels -> 320: the 8-channel tail segment fills one chunk
+        "gen.fp.backward_1.offset.0", "gen.fp.forward_1.offset.0", "gen.fp.backward_1.backbone.0",
+        "gen.fp.forward_1.backbone.0", "gen.fp.fuse.0")
 
     def load_weights(self, raft_sd, rfc_sd, gen_sd):
         convs, tens = build_layers(raft_sd, rfc_sd, gen_sd)
         for name, (w, b, groups, cin_map) in convs.items():
-            if name in self.PAD64_CONVS and cin_map is None and w.shape[1] % 64 != 0:
-                cin_map = _pad_map(w.shape[1], (w.shape[1] + 63) // 64 * 64)
+            if name in self.PAD64_CONVS:
+                cin_map = list(cin_map) if cin_map is not None else list(range(w.shape[1]))
+                cin_map += [-1] * ((-len(cin_map)) % 64)
             self.register_conv(name, w, b, groups, cin_map)
         for name, t in tens.items():
             self.register_tensor(name, t)

@@ -54,16 +54,7 @@ def test_pack_conv_weight_roundtrip(cout, cin, k, groups, cin_pad):
 def test_build_layers_covers_checkpoints():
     convs, tens = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
                                  Wt.synthetic_generator_state_dict())
-    split = [n for n in convs if n.endswith((".main", ".tail"))]
-    assert len(convs) - len(split) == 150 and len(split) == 10 and len(tens) == 8 * 6
-    # "<name>.main" + "<name>.tail" partition the kernel channels of "<name>" (64-aligned part | mask/flow tail)
-    for n in split:
-        if n.endswith(".main"):
-            base = n[:-5]
-            w, b, _, cmap = convs[base]
-            cm, ct = convs[n][3], convs[base + ".tail"][3]
-            assert cm + ct == cmap and len(cm) % 64 == 0 and len(ct) == 8
-            assert convs[n][1] is None and torch.equal(convs[base + ".tail"][1], b)
+    assert len(convs) == 150 and len(tens) == 8 * 6
     # every kernel-side input channel count is a multiple of 8
     for name, (w, b, groups, cmap) in convs.items():
         cin = len(cmap) if cmap is not None else w.shape[1]
