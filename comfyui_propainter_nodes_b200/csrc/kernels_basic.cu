@@ -29,41 +29,73 @@ __global__ void nhwc_f16_to_nchw_f32(const __half* __restrict__ src, int src_cs,
 }
 
 // Bilinear x2 upsample, align_corners=True (reference deconv: F.interpolate(scale_factor=2, 'bilinear', True)).
-// One thread per (output pixel, 8-channel vector); grid = (x chunks, output rows, images) so all index math is
-// 32-bit and the row interpolation is uniform per block.
+// One thread per (2x2 block of output pixels, 8-channel vector).  With scale (H-1)/(2H-1) < 1/2 the outputs of block
+// (r, c) interpolate between input rows (r-1, r) / (r, r+1) and columns (c-1, c) / (c, c+1): interior blocks load and
+// convert the 3x3 neighbourhood once (9 loads for 4 outputs); blocks where the floor() of a source coordinate is not
+// the canonical one (image borders, float rounding) take the generic 4-loads-per-output path.  Per output the
+// arithmetic is w00*a + w01*b + w10*c + w11*d in fp32 with one rounding on both paths.
+// grid = (x chunks, block rows, images): all index math is 32-bit.
+__device__ __forceinline__ void up8(const uint4& q, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(h[e]);
+    f[2 * e] = t.x; f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void up_store(__half* dp, const float (&a)[8], const float (&b)[8], const float (&c)[8],
+                                         const float (&d)[8], float ly, float lx) {
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  __align__(16) __half2 o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    o[e] = __floats2half2_rn(w00 * a[2 * e] + w01 * b[2 * e] + w10 * c[2 * e] + w11 * d[2 * e],
+                             w00 * a[2 * e + 1] + w01 * b[2 * e + 1] + w10 * c[2 * e + 1] + w11 * d[2 * e + 1]);
+  *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<uint4*>(o);
+}
 __global__ void __launch_bounds__(256) upsample2x_ac(const __half* __restrict__ src, int src_cs, int src_co,
                                                      __half* __restrict__ dst, int dst_cs, int dst_co, int H, int W, int C8) {
   const int OW = 2 * W, OH = 2 * H;
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (unsigned)(OW * C8)) return;
-  const int c8 = idx % (unsigned)C8, ox = idx / (unsigned)C8;
-  const int oy = blockIdx.y, n = blockIdx.z;
+  if (idx >= (unsigned)(W * C8)) return;
+  const int c8 = idx % (unsigned)C8, c = idx / (unsigned)C8;   // block column
+  const int r = blockIdx.y, n = blockIdx.z;                    // block row, image
   const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f;
   const float sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
-  const float fy = sy * oy, fx = sx * ox;
-  const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-  const float ly = fy - y0, lx = fx - x0;
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const float fy0 = sy * (float)(2 * r), fy1 = sy * (float)(2 * r + 1);
+  const float fx0 = sx * (float)(2 * c), fx1 = sx * (float)(2 * c + 1);
+  const int ay0 = (int)fy0, ay1 = (int)fy1, ax0 = (int)fx0, ax1 = (int)fx1;
   const __half* base = src + (long long)n * H * W * src_cs + src_co + c8 * 8;
-  const uint4 a = *reinterpret_cast<const uint4*>(base + (long long)(y0 * W + x0) * src_cs);
-  const uint4 b = *reinterpret_cast<const uint4*>(base + (long long)(y0 * W + x1) * src_cs);
-  const uint4 c = *reinterpret_cast<const uint4*>(base + (long long)(y1 * W + x0) * src_cs);
-  const uint4 d = *reinterpret_cast<const uint4*>(base + (long long)(y1 * W + x1) * src_cs);
-  const __half2* ah = reinterpret_cast<const __half2*>(&a);
-  const __half2* bh = reinterpret_cast<const __half2*>(&b);
-  const __half2* ch = reinterpret_cast<const __half2*>(&c);
-  const __half2* dh = reinterpret_cast<const __half2*>(&d);
-  __align__(16) __half2 o[4];
+  __half* dbase = dst + (long long)n * OH * OW * dst_cs + dst_co + c8 * 8;
+  if (ay0 == r - 1 && ay1 == r && r + 1 < H && ax0 == c - 1 && ax1 == c && c + 1 < W && r > 0 && c > 0) {
+    float v[3][3][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 fa = __half22float2(ah[i]), fb = __half22float2(bh[i]), fc = __half22float2(ch[i]),
-                 fd = __half22float2(dh[i]);
-    o[i] = __floats2half2_rn(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
-                             w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        up8(*reinterpret_cast<const uint4*>(base + (long long)((r - 1 + j) * W + (c - 1 + i)) * src_cs), v[j][i]);
+    const float ly0 = fy0 - (float)ay0, ly1 = fy1 - (float)ay1, lx0 = fx0 - (float)ax0, lx1 = fx1 - (float)ax1;
+    __half* d0 = dbase + ((long long)(2 * r) * OW + 2 * c) * dst_cs;
+    up_store(d0, v[0][0], v[0][1], v[1][0], v[1][1], ly0, lx0);
+    up_store(d0 + dst_cs, v[0][1], v[0][2], v[1][1], v[1][2], ly0, lx1);
+    up_store(d0 + (long long)OW * dst_cs, v[1][0], v[1][1], v[2][0], v[2][1], ly1, lx0);
+    up_store(d0 + (long long)(OW + 1) * dst_cs, v[1][1], v[1][2], v[2][1], v[2][2], ly1, lx1);
+    return;
   }
-  __half* dp = dst + (((long long)n * OH + oy) * OW + ox) * dst_cs + dst_co + c8 * 8;
-  *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<uint4*>(o);
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float fy = dy ? fy1 : fy0, fx = dx ? fx1 : fx0;
+      const int y0 = dy ? ay1 : ay0, x0 = dx ? ax1 : ax0;
+      const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+      float a[8], b[8], cc[8], d[8];
+      up8(*reinterpret_cast<const uint4*>(base + (long long)(y0 * W + x0) * src_cs), a);
+      up8(*reinterpret_cast<const uint4*>(base + (long long)(y0 * W + x1) * src_cs), b);
+      up8(*reinterpret_cast<const uint4*>(base + (long long)(y1 * W + x0) * src_cs), cc);
+      up8(*reinterpret_cast<const uint4*>(base + (long long)(y1 * W + x1) * src_cs), d);
+      up_store(dbase + ((long long)(2 * r + dy) * OW + 2 * c + dx) * dst_cs, a, b, cc, d, fy - (float)y0, fx - (float)x0);
+    }
 }
 
 __global__ void copy_channels(const __half* __restrict__ src, int src_cs, int src_co, __half* __restrict__ dst,
@@ -116,8 +148,8 @@ int pp_k_upsample2x(const __half* src, int src_cs, int src_co, __half* dst, int 
   PP_REQUIRE(C % 8 == 0 && src_cs % 8 == 0 && dst_cs % 8 == 0 && src_co % 8 == 0 && dst_co % 8 == 0,
              "upsample2x: channels must be multiples of 8");
   if ((long long)N * H * W == 0) return PP_OK;
-  PP_REQUIRE(2 * H <= 65535 && N <= 65535, "upsample2x: %d rows / %d images exceed the grid limits", 2 * H, N);
-  const dim3 grid(pp_ceil_div(2 * W * (C / 8), 256), 2 * H, N);
+  PP_REQUIRE(H <= 65535 && N <= 65535, "upsample2x: %d rows / %d images exceed the grid limits", H, N);
+  const dim3 grid(pp_ceil_div(W * (C / 8), 256), H, N);
   upsample2x_ac<<<grid, 256, 0, st>>>(src, src_cs, src_co, dst, dst_cs, dst_co, H, W, C / 8);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;

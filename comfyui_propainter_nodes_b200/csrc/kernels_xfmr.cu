@@ -12,56 +12,65 @@ inline int nblocks(long long n, int per = TPB) { return (int)((n + per - 1) / pe
 // Rows are re-mapped from the [t][gh][gw] token grid into the zero-padded [t][nh][nw] grid the window
 // attention works on (padding tokens stay zero *before* the Q/K/V linears, sparse_transformer.py:212-221).
 // ------------------------------------------------------------------------------------------------
-__global__ void layernorm512(const __half* __restrict__ x, const float* __restrict__ gamma,
-                             const float* __restrict__ beta, __half* __restrict__ out, long long rows, int gh, int gw,
-                             int nh, int nw) {
-  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(256) layernorm512(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, __half* __restrict__ out, long long rows,
+                                                    int gh, int gw, int nh, int nw) {
+  // one warp per row, rows strided by the number of warps in the grid; lane l always owns channels 16l..16l+15, so
+  // its gamma / beta values are loaded once into registers instead of once per row (they were 80 % of the L1 traffic)
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const uint4* xp = reinterpret_cast<const uint4*>(x + row * 512) + lane * 2;
-  uint4 raw[2] = {xp[0], xp[1]};
-  float v[16];
-  const __half2* h = reinterpret_cast<const __half2*>(raw);
-  float s = 0.f, q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 f = __half22float2(h[i]);
-    v[2 * i] = f.x; v[2 * i + 1] = f.y;
-    s += f.x + f.y;
-    q += f.x * f.x + f.y * f.y;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
-  }
-  const float mean = s * (1.f / 512.f);
-  const float var = fmaxf(q * (1.f / 512.f) - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + 1e-5f);
-  __align__(16) __half2 o2[8];
-  const float4* g4 = reinterpret_cast<const float4*>(gamma) + lane * 4;
-  const float4* b4 = reinterpret_cast<const float4*>(beta) + lane * 4;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float g[16], bt[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 gg = __ldg(g4 + i), bb = __ldg(b4 + i);
-    o2[2 * i] = __floats2half2_rn((v[4 * i] - mean) * rstd * gg.x + bb.x, (v[4 * i + 1] - mean) * rstd * gg.y + bb.y);
-    o2[2 * i + 1] = __floats2half2_rn((v[4 * i + 2] - mean) * rstd * gg.z + bb.z, (v[4 * i + 3] - mean) * rstd * gg.w + bb.w);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + lane * 4 + i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + lane * 4 + i);
+    g[4 * i] = gg.x; g[4 * i + 1] = gg.y; g[4 * i + 2] = gg.z; g[4 * i + 3] = gg.w;
+    bt[4 * i] = bb.x; bt[4 * i + 1] = bb.y; bt[4 * i + 2] = bb.z; bt[4 * i + 3] = bb.w;
   }
-  long long orow = row;
-  if (nh != gh || nw != gw) {
-    const int xx = row % gw;
-    const long long t = row / gw;
-    const int yy = t % gh;
-    const long long f = t / gh;
-    orow = (f * nh + yy) * nw + xx;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const uint4* xp = reinterpret_cast<const uint4*>(x + row * 512) + lane * 2;
+    uint4 raw[2] = {xp[0], xp[1]};
+    float v[16];
+    const __half2* h = reinterpret_cast<const __half2*>(raw);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      s += f.x + f.y;
+      q += f.x * f.x + f.y * f.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const float mean = s * (1.f / 512.f);
+    const float var = fmaxf(q * (1.f / 512.f) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    __align__(16) __half2 o2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o2[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * g[2 * i] + bt[2 * i],
+                                (v[2 * i + 1] - mean) * rstd * g[2 * i + 1] + bt[2 * i + 1]);
+    long long orow = row;
+    if (nh != gh || nw != gw) {
+      const int xx = row % gw;
+      const long long t = row / gw;
+      const int yy = t % gh;
+      const long long f = t / gh;
+      orow = (f * nh + yy) * nw + xx;
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + orow * 512) + lane * 2;
+    op[0] = reinterpret_cast<uint4*>(o2)[0];
+    op[1] = reinterpret_cast<uint4*>(o2)[1];
   }
-  uint4* op = reinterpret_cast<uint4*>(out + orow * 512) + lane * 2;
-  op[0] = reinterpret_cast<uint4*>(o2)[0];
-  op[1] = reinterpret_cast<uint4*>(o2)[1];
 }
 
+// ------------------------------------------------------------------------------------------------
 // Learned depthwise 4x4 stride-4 pooling of the (padded, normalised) tokens (pool_layer,
-// sparse_transformer.py:176-180, 294-297).  x [t][nh][nw][C] -> out [t][ph][pw][C]; w [C][16] fp32.
+// sparse_transformer.py:176-180, 294-297).  x [t][nh][nw][C] -> out [t][ph][pw][C]; w [16 taps][C] fp32.
 __global__ void __launch_bounds__(256) pool_tokens(const __half* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ b, __half* __restrict__ out, int nh, int nw,
                                                    int ph, int pw, int C) {
@@ -139,28 +148,41 @@ __global__ void fold7x7s3(const __half* __restrict__ x, int cs, __half* __restri
   const int c8 = idx % (unsigned)C8, px = idx / (unsigned)C8;
   const int py = blockIdx.y, f = blockIdx.z;
   (void)t;
+  // a pixel is covered by at most 3x3 patches (7x7 patches, stride 3): all nine 16-byte loads are issued up front
+  // (predicated), then accumulated in the original order (descending token row / column)
+  const int ty1 = min((py + 3) / 3, gh - 1), tx1 = min((px + 3) / 3, gw - 1);
+  uint4 q[9];
+  bool ok[9];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int ty = ty1 - a, ky = py + 3 - 3 * ty;
+    const bool vy = ty >= 0 && ky <= 6;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int tx = tx1 - b, kx = px + 3 - 3 * tx;
+      const bool v = vy && tx >= 0 && kx <= 6;
+      ok[a * 3 + b] = v;
+      q[a * 3 + b] = make_uint4(0, 0, 0, 0);
+      if (v)
+        q[a * 3 + b] = *reinterpret_cast<const uint4*>(x + (((long long)f * gh + ty) * gw + tx) * cs +
+                                                       (ky * 7 + kx) * C + c8 * 8);
+    }
+  }
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   int cnt = 0;
-  const int ty1 = min((py + 3) / 3, gh - 1), tx1 = min((px + 3) / 3, gw - 1);
-  for (int ty = ty1; ty >= 0; --ty) {
-    const int ky = py + 3 - 3 * ty;
-    if (ky > 6) break;
-    for (int tx = tx1; tx >= 0; --tx) {
-      const int kx = px + 3 - 3 * tx;
-      if (kx > 6) break;
-      const uint4 q = *reinterpret_cast<const uint4*>(x + (((long long)f * gh + ty) * gw + tx) * cs +
-                                                      (ky * 7 + kx) * C + c8 * 8);
-      const __half2* hq = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 v = __half22float2(hq[e]);
-        acc[2 * e] += v.x;
-        acc[2 * e + 1] += v.y;
-      }
-      ++cnt;
+  for (int t = 0; t < 9; ++t) {
+    if (!ok[t]) continue;
+    const __half2* hq = reinterpret_cast<const __half2*>(&q[t]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 v = __half22float2(hq[e]);
+      acc[2 * e] += v.x;
+      acc[2 * e + 1] += v.y;
     }
+    ++cnt;
   }
   const float inv = (normalise && cnt > 0) ? 1.f / (float)cnt : 1.f;
   __align__(16) __half2 o[4];
@@ -206,7 +228,11 @@ __global__ void composite(const __half* __restrict__ pred, int pred_cs, const fl
 int pp_k_layernorm(const __half* x, const float* gamma, const float* beta, __half* out, long long rows, int gh, int gw,
                    int nh, int nw, cudaStream_t st) {
   if (rows == 0) return PP_OK;
-  layernorm512<<<nblocks(rows * 32), TPB, 0, st>>>(x, gamma, beta, out, rows, gh, gw, nh, nw);
+  {
+    const long long want = (rows + 7) / 8;                 // 8 rows (warps) per block
+    const int grid = (int)(want < 148 * 32 ? want : 148 * 32);   // a few rows per warp: gamma/beta loads amortised
+    layernorm512<<<grid, 256, 0, st>>>(x, gamma, beta, out, rows, gh, gw, nh, nw);
+  }
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }
