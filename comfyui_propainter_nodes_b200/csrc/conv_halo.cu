@@ -29,6 +29,10 @@ namespace {
 constexpr int NUM_THREADS = 352;
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int WARP_A = 8, WARP_B = 9, WARP_MMA = 10;
+// fused x2-upsample variant (UPS): warps 8-11 interpolate the input patch (warp 8 also issues the low-res TMA loads),
+// the weight producer and the MMA issuer move to warps 12 / 13
+constexpr int UPS_THREADS = 448, UPS_INTERP_THREADS = 128;
+constexpr int UPS_WARP_B = 12, UPS_WARP_MMA = 13;
 constexpr int MAX_SA = 4, MAX_SB = 8;
 constexpr int SMEM_BUDGET = 208 * 1024;
 
@@ -44,6 +48,10 @@ struct HaloParams {
   int flat;          // 1x1 convs: tiles are runs of 128*MT consecutive pixels of the flattened [N*H*W] pixel list
   int n_img;         // images the tile index decomposes over (1 in flat mode)
   int sub_bytes;     // A-view offset between the sub-tiles: 8 pixels (spatial) or 128 pixels (flat)
+  int ups;           // input tensor is half resolution: bilinear x2 (align_corners) on the fly (UPS kernel)
+  int LH, LW;        // low-res source size
+  int LBW, LBH;      // low-res staging box (pixels)
+  int l_stage_bytes;
   int debug;         // bit 0: skip the epilogue math/stores (PP_CONV_NOEPI=1, mainloop-only timing experiments)
 };
 
@@ -68,7 +76,8 @@ __device__ __forceinline__ TileCoord decode_tile(const HaloParams& h, int tile) 
   return t;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams h) {
+template <bool UPS>
+__global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_kernel(const __grid_constant__ HaloParams h) {
   using namespace ppx;
   const PPConvParams& p = h.c;
   extern __shared__ uint8_t smem_raw[];
@@ -81,7 +90,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
   uint64_t* b_empty = b_full + MAX_SB;
   uint64_t* acc_full = b_empty + MAX_SB;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* l_full = acc_empty + 2;     // UPS: low-res staging ring (2 stages)
+  uint64_t* l_empty = l_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_empty + 2);
+  constexpr int W_B = UPS ? UPS_WARP_B : WARP_B, W_MMA = UPS ? UPS_WARP_MMA : WARP_MMA;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * p.groups;
@@ -91,12 +103,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
   while (tmem_cols < 2 * set_cols) tmem_cols <<= 1;
 
   if (tid == 0) {
-    for (int s = 0; s < h.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < h.SA; ++s) { mbar_init(&a_full[s], UPS ? UPS_INTERP_THREADS : 1); mbar_init(&a_empty[s], 1); }
+    if (UPS) for (int s = 0; s < 2; ++s) { mbar_init(&l_full[s], 1); mbar_init(&l_empty[s], UPS_INTERP_THREADS); }
     for (int s = 0; s < h.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], NUM_EPI_THREADS); }
     mbar_fence_init();
   }
-  if (warp == WARP_MMA) {
+  if (warp == W_MMA) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
@@ -169,7 +182,98 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         mbar_arrive(&acc_empty[set]);
       }
     }
-  } else if (warp == WARP_A) {
+  } else if (UPS && warp < 12) {
+    // ------------------------------------------------------------------ fused bilinear x2 (align_corners=True) producer
+    // The conv's input is the x2 upsampling of a half-resolution tensor (reference deconv = F.interpolate + conv).
+    // Per 64-channel chunk the elected lane of warp 8 TMA-loads the low-res patch that covers the 18x18 hi-res patch
+    // into a 2-stage staging ring; the 128 threads interpolate it (fp32, one rounding, same expression as the
+    // stand-alone upsample kernel) straight into the 128B-swizzled A stage.  Hi-res pixels outside the image are the
+    // conv's zero padding.  The upsampled tensor (4x the pixels) never exists in memory.
+    const int it_id = tid - 256;
+    uint8_t* stg = smem_b + h.SB * h.b_stage_bytes + 1024;     // staging ring behind the barrier block
+    const float sy = (float)(h.LH - 1) / (float)(2 * h.LH - 1), sx = (float)(h.LW - 1) / (float)(2 * h.LW - 1);
+    const uint32_t lbytes = (uint32_t)(h.LBW * h.LBH * 128);
+    const bool issuer = warp == 8 && elect_one();
+    auto low_origin = [&](const TileCoord& t, int& xlo, int& ylo) {
+      const int X0 = t.tx * (8 * h.MT) - p.pw, Y0 = t.ty * 16 - p.ph;
+      xlo = (int)(sx * (float)max(X0, 0));
+      ylo = (int)(sy * (float)max(Y0, 0));
+    };
+    auto issue = [&](int tile, int c, int ls, uint32_t lph) {
+      const TileCoord t = decode_tile(h, tile);
+      int xlo, ylo;
+      low_origin(t, xlo, ylo);
+      mbar_wait(&l_empty[ls], lph ^ 1);
+      mbar_arrive_expect_tx(&l_full[ls], lbytes);
+      tma_load_4d(smem_u32(stg + ls * h.l_stage_bytes), &h.tmap[0], c * 64, xlo, ylo, t.img, &l_full[ls]);
+    };
+    int ls = 0, sa = 0;
+    uint32_t lph = 0, pa = 0;
+    // producer-side schedule of staging slots: (stage, phase) advance once per issued chunk
+    int is_ls = 0;
+    uint32_t is_ph = 0;
+    if (issuer && blockIdx.x < total_tiles) {
+      issue(blockIdx.x, 0, is_ls, is_ph);
+      if (++is_ls == 2) { is_ls = 0; is_ph ^= 1; }
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(h, tile);
+      const int X0 = t.tx * (8 * h.MT) - p.pw, Y0 = t.ty * 16 - p.ph;
+      int xlo, ylo;
+      low_origin(t, xlo, ylo);
+      for (int c = 0; c < h.chunks; ++c) {
+        if (issuer) {   // prefetch the next chunk's low-res patch
+          int nt = tile, nc = c + 1;
+          if (nc == h.chunks) { nc = 0; nt += gridDim.x; }
+          if (nt < total_tiles) {
+            issue(nt, nc, is_ls, is_ph);
+            if (++is_ls == 2) { is_ls = 0; is_ph ^= 1; }
+          }
+        }
+        __syncwarp();
+        mbar_wait(&l_full[ls], lph);
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        const uint8_t* src = stg + ls * h.l_stage_bytes;
+        uint8_t* dstA = smem + sa * h.a_stage_bytes;
+        const int items = h.BW * h.BH * 8;
+        for (int item = it_id; item < items; item += UPS_INTERP_THREADS) {
+          const int ch = item & 7, pp = item >> 3;
+          const int py = pp / h.BW, px = pp - py * h.BW;
+          const int Y = Y0 + py, X = X0 + px;
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if ((unsigned)Y < (unsigned)(2 * h.LH) && (unsigned)X < (unsigned)(2 * h.LW)) {
+            const float fy = sy * (float)Y, fx = sx * (float)X;
+            const int y0 = (int)fy, x0 = (int)fx;
+            const int y1 = min(y0 + 1, h.LH - 1), x1 = min(x0 + 1, h.LW - 1);
+            const float ly = fy - (float)y0, lx = fx - (float)x0;
+            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+            const uint8_t* r0 = src + ((y0 - ylo) * h.LBW - xlo) * 128 + ch * 16;
+            const uint8_t* r1 = src + ((y1 - ylo) * h.LBW - xlo) * 128 + ch * 16;
+            const uint4 qa = *reinterpret_cast<const uint4*>(r0 + x0 * 128), qb = *reinterpret_cast<const uint4*>(r0 + x1 * 128);
+            const uint4 qc = *reinterpret_cast<const uint4*>(r1 + x0 * 128), qd = *reinterpret_cast<const uint4*>(r1 + x1 * 128);
+            const __half2* ah = reinterpret_cast<const __half2*>(&qa);
+            const __half2* bh = reinterpret_cast<const __half2*>(&qb);
+            const __half2* chh = reinterpret_cast<const __half2*>(&qc);
+            const __half2* dh = reinterpret_cast<const __half2*>(&qd);
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 fa = __half22float2(ah[i]), fb = __half22float2(bh[i]), fc = __half22float2(chh[i]),
+                           fd = __half22float2(dh[i]);
+              oh[i] = __floats2half2_rn(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x,
+                                        w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(dstA + pp * 128 + ((ch ^ (pp & 7)) << 4)) = o;
+        }
+        fence_proxy_async();            // generic-proxy writes of the A stage -> visible to tcgen05.mma
+        mbar_arrive(&a_full[sa]);
+        mbar_arrive(&l_empty[ls]);
+        if (++ls == 2) { ls = 0; lph ^= 1; }
+        if (++sa == h.SA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (!UPS && warp == WARP_A) {
     // ------------------------------------------------------------------ input patch producer (TMA)
     if (ppx::elect_one()) {
       int s = 0;
@@ -192,7 +296,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         }
       }
     }
-  } else if (warp == WARP_B) {
+  } else if (warp == W_B) {
     // ------------------------------------------------------------------ weight tile producer (bulk copy)
     if (ppx::elect_one()) {
       int s = 0;
@@ -213,7 +317,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
         }
       }
     }
-  } else if (warp == WARP_MMA) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     // One elected lane (elect.sync lets ptxas emit each tcgen05.mma once instead of a per-lane loop).  The loop is
     // kept lean -- descriptors advance by precomputed 16-byte-unit steps -- because a single thread has to issue
@@ -276,7 +380,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_halo_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == WARP_MMA) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == W_MMA) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -323,6 +427,7 @@ int pp_conv_halo_eligible(const PPConvParams& p) {
   }
   if ((p.kw - 1) * p.dw + 16 > 256 || (p.kh - 1) * p.dh + 16 > 256) return 0;
   if ((long long)p.N * p.OH * p.OW < 128) return 0;
+  if (p.ups2x && (flat || p.nseg != 1 || p.groups != 1 || p.H % 2 != 0 || p.W % 2 != 0 || p.H < 4 || p.W < 4)) return 0;
   return encode_fn() != nullptr ? 1 : 0;
 }
 
@@ -335,7 +440,8 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
     int dev = 0;
     PP_CUDA_CHECK(cudaGetDevice(&dev));
     PP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   }
   const bool flat = p.kh * p.kw == 1;
   // N tile: <= 128 columns (two accumulator sets x two sub-tiles fill the 512 TMEM columns)
@@ -348,7 +454,7 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
     return (long long)pp_ceil_div(p.Cout_g_pad, bn_) * tiles_x(mt) * tiles_y * n_img * p.groups;
   };
   int mt = 2;
-  if (count(2, bn) < num_sms) mt = 1;
+  if (!p.ups2x && count(2, bn) < num_sms) mt = 1;
   while (count(mt, bn) < num_sms && bn >= 64 && bn % 32 == 0) bn /= 2;   // small launches: more, narrower tiles
   p.BN = bn;
   h.MT = mt;
@@ -364,14 +470,19 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
   h.accw = pp_ceil_div(bn, 32) * 32;
   h.a_stage_bytes = pp_ceil_div(h.BW * h.BH * 128, 1024) * 1024;
   h.b_stage_bytes = bn * 128;
-  int sa = 3, sb = 0;
+  h.ups = p.ups2x ? 1 : 0;
+  h.LH = p.H / 2; h.LW = p.W / 2;
+  h.LBW = (h.BW - 1) / 2 + 3; h.LBH = (h.BH - 1) / 2 + 3;      // low-res pixels that can feed BW x BH hi-res ones
+  h.l_stage_bytes = h.ups ? pp_ceil_div(h.LBW * h.LBH * 128, 1024) * 1024 : 0;
+  const int budget = SMEM_BUDGET - 2 * h.l_stage_bytes - (h.ups ? 1024 : 0);
+  int sa = h.ups ? 2 : 3, sb = 0;
   for (; sa >= 2; --sa) {
-    sb = (SMEM_BUDGET - sa * h.a_stage_bytes) / h.b_stage_bytes;
+    sb = (budget - sa * h.a_stage_bytes) / h.b_stage_bytes;
     if (sb >= 3) break;
   }
   PP_REQUIRE(sa >= 2 && sb >= 3, "conv_halo: patch %dx%d does not fit shared memory", h.BW, h.BH);
   if (sb > MAX_SB) sb = MAX_SB;
-  if (sa == 3 && sb == MAX_SB && (SMEM_BUDGET - 4 * h.a_stage_bytes) / h.b_stage_bytes >= MAX_SB) sa = 4;
+  if (!h.ups && sa == 3 && sb == MAX_SB && (budget - 4 * h.a_stage_bytes) / h.b_stage_bytes >= MAX_SB) sa = 4;
   h.SA = sa; h.SB = sb;
   { const char* e = getenv("PP_CONV_NOEPI"); h.debug = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
   const long long total_tiles = count(mt, bn);
@@ -389,19 +500,25 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
       dims[1] = (cuuint64_t)p.M_total; dims[2] = 1; dims[3] = 1;
       strides[1] = strides[2] = (cuuint64_t)p.M_total * s.cstride * 2;
     }
+    if (h.ups) {  // the tensor in memory is the half-resolution source; it lands unswizzled in the staging ring
+      dims[1] = (cuuint64_t)h.LW; dims[2] = (cuuint64_t)h.LH;
+      strides[1] = (cuuint64_t)h.LW * s.cstride * 2; strides[2] = (cuuint64_t)h.LH * h.LW * s.cstride * 2;
+      box[1] = (cuuint32_t)h.LBW; box[2] = (cuuint32_t)h.LBH;
+    }
     cuuint32_t es[4] = {1, 1, 1, 1};
     const CUresult r = enc(&h.tmap[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(s.ptr + s.coff), dims, strides, box,
-                           es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           es, CU_TENSOR_MAP_INTERLEAVE_NONE, h.ups ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PP_REQUIRE(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled failed (%d) for segment %d (cstride=%d W=%d H=%d N=%d)",
                (int)r, i, s.cstride, p.W, p.H, p.N);
   }
-  const size_t smem = (size_t)sa * h.a_stage_bytes + (size_t)sb * h.b_stage_bytes + 1024 + 512;
+  const size_t smem = (size_t)sa * h.a_stage_bytes + (size_t)sb * h.b_stage_bytes + 1024 + 512 + 2 * (size_t)h.l_stage_bytes +
+                      (h.ups ? 1024 : 0);
   const int grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(h.ups ? UPS_THREADS : NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -409,7 +526,8 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel, h));
+  if (h.ups) PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, h));
+  else PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<false>, h));
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

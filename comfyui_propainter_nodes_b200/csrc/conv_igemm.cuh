@@ -36,6 +36,7 @@ struct PPConvParams {
   int Cin;                // per-group input channels as seen by the kernel (multiple of 8)
   int kh, kw, sh, sw, ph, pw, dh, dw;
   int pad_replicate;      // 0: zeros outside, 1: clamp coordinates (replicate padding)
+  int ups2x;              // the input tensor is [N][H/2][W/2]: bilinear x2 (align_corners=True) on the fly (halo kernel only)
   int K_total;            // kh*kw*Cin
   int num_kc;             // ceil(K_total / 64)
   int M_total;            // N*OH*OW

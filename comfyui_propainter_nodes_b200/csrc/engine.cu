@@ -1,4 +1,5 @@
 // Engine plumbing: registries and the conv-call builder.
+#include <stdlib.h>
 #include <string.h>
 
 #include "engine.cuh"
@@ -52,6 +53,17 @@ PPConvCall& PPConvCall::in(const __half* ptr, int cs, int co, int channels, int 
 
 PPConvCall& PPConvCall::geom(int sh, int sw, int ph, int pw, int dh, int dw, int replicate) {
   p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw; p.dh = dh; p.dw = dw; p.pad_replicate = replicate;
+  return *this;
+}
+
+int pp_fuse_upsample() {
+  // read on every call (a getenv per deconv layer is noise) so tests can exercise both paths in one process
+  const char* s = getenv("PP_FUSE_UPSAMPLE");
+  return (s != nullptr && atoi(s) != 0) ? 1 : 0;
+}
+
+PPConvCall& PPConvCall::upsampled2x() {
+  p.ups2x = 1;
   return *this;
 }
 

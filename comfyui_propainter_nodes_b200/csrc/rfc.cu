@@ -138,19 +138,34 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
   PP_TRY(pp_alloc(e, &pred, (size_t)N * HW * 2, "rfc pred"));
   PP_TRY(PPConvCall(e, "rfc.decoder2.0", N, h8, w8).in(fused, 128, 0, 128).out(d2a, 128, 0)
              .act(PP_ACT_LRELU, 0.2f).run(st));
-  PP_TRY(pp_k_upsample2x(d2a, 128, 0, up, 128, 0, N, h8, w8, 128, st));
-  PP_TRY(PPConvCall(e, "rfc.decoder2.deconv", N, h4, w4).in(up, 128, 0, 128).out(d2, 64, 0)
-             .act(PP_ACT_LRELU, 0.2f).residual(e1, 64, 0).run(st));
+  const bool fuse = pp_fuse_upsample() != 0;   // deconv = bilinear x2 + 3x3 conv in one launch (halo kernel, UPS variant)
+  if (fuse) {
+    PP_TRY(PPConvCall(e, "rfc.decoder2.deconv", N, h4, w4).in(d2a, 128, 0, 128).upsampled2x().out(d2, 64, 0)
+               .act(PP_ACT_LRELU, 0.2f).residual(e1, 64, 0).run(st));
+  } else {
+    PP_TRY(pp_k_upsample2x(d2a, 128, 0, up, 128, 0, N, h8, w8, 128, st));
+    PP_TRY(PPConvCall(e, "rfc.decoder2.deconv", N, h4, w4).in(up, 128, 0, 128).out(d2, 64, 0)
+               .act(PP_ACT_LRELU, 0.2f).residual(e1, 64, 0).run(st));
+  }
   PP_TRY(PPConvCall(e, "rfc.decoder1.0", N, h4, w4).in(d2, 64, 0, 64).out(d1a, 64, 0).act(PP_ACT_LRELU, 0.2f).run(st));
-  PP_TRY(pp_k_upsample2x(d1a, 64, 0, up, 64, 0, N, h4, w4, 64, st));
-  PP_TRY(PPConvCall(e, "rfc.decoder1.deconv", N, h2, w2).in(up, 64, 0, 64).out(d1, 32, 0)
-             .act(PP_ACT_LRELU, 0.2f).run(st));
+  if (fuse) {
+    PP_TRY(PPConvCall(e, "rfc.decoder1.deconv", N, h2, w2).in(d1a, 64, 0, 64).upsampled2x().out(d1, 32, 0)
+               .act(PP_ACT_LRELU, 0.2f).run(st));
+  } else {
+    PP_TRY(pp_k_upsample2x(d1a, 64, 0, up, 64, 0, N, h4, w4, 64, st));
+    PP_TRY(PPConvCall(e, "rfc.decoder1.deconv", N, h2, w2).in(up, 64, 0, 64).out(d1, 32, 0)
+               .act(PP_ACT_LRELU, 0.2f).run(st));
+  }
   PP_TRY(PPConvCall(e, "rfc.upsample.0", N, h2, w2).in(d1, 32, 0, 32).out(u0, 32, 0).act(PP_ACT_LRELU, 0.2f).run(st));
-  PP_TRY(pp_k_upsample2x(u0, 32, 0, up, 32, 0, N, h2, w2, 32, st));
+  if (!fuse) PP_TRY(pp_k_upsample2x(u0, 32, 0, up, 32, 0, N, h2, w2, 32, st));
   // 32->2 tail: per-tap partial products (fp32 scratch) + tap gather
   float* ztap;
   PP_TRY(pp_alloc(e, &ztap, (size_t)N * HW * 32, "rfc tap products"));
-  PP_TRY(pp_small_conv(e, "rfc.upsample.deconv", up, 32, 0, 32, 2, ztap, 1, pred, 2, 0, 0, 0, N, H, W, st));
+  if (fuse) {
+    PP_TRY(PPConvCall(e, "rfc.upsample.deconv", N, H, W).in(u0, 32, 0, 32).upsampled2x().out(pred, 2, 0).run(st));
+  } else {
+    PP_TRY(pp_small_conv(e, "rfc.upsample.deconv", up, 32, 0, 32, 2, ztap, 1, pred, 2, 0, 0, 0, N, H, W, st));
+  }
   e.launches += 3;
 
   // ---- combine_flow (:389-400) and un-flip ----------------------------------------------------------
