@@ -117,7 +117,7 @@ struct CorrLevels {
 //   out[l*81 + i*9 + j] = bilerp(T_l[j..j+1][i..i+1])      (i moves x, j moves y -- the meshgrid quirk)
 // Taps are fetched as aligned fp16 pairs (12 columns starting at the even column <= x0-4; map widths are even at
 // every level for the sizes ProPainter produces, odd widths take the scalar path), which halves the load
-// instructions; output channel -> (level, tap offset) comes from a small table built once per block.
+// instructions; the output loop runs level by level with the level's fractions in registers.
 // Global traffic per pixel = the algorithmic 8 B coords + 4x100 taps + 324 outputs; stores are contiguous.
 constexpr int LOOKUP_WARPS = 8;
 constexpr int TAP_COLS = 12;   // staged columns per tap row
@@ -127,22 +127,12 @@ __global__ void __launch_bounds__(LOOKUP_WARPS * 32) corr_lookup(CorrLevels lv, 
                                                                  __half* __restrict__ out, int out_cs, long long nq,
                                                                  int h8, int w8) {
   __shared__ float taps[LOOKUP_WARPS][4][TAP_STRIDE];
-  __shared__ float frac[LOOKUP_WARPS][4][2];
-  __shared__ int phase[LOOKUP_WARPS][4];
-  __shared__ unsigned short otab[352];
-  for (int c = threadIdx.x; c < 352; c += blockDim.x) {
-    unsigned short e = 0xFFFF;
-    if (c < 324) {
-      const int l = c / 81, r = c - l * 81, i = r / 9, j = r - i * 9;
-      e = (unsigned short)((l << 12) | (j * TAP_COLS + i));
-    }
-    otab[c] = e;
-  }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = (long long)blockIdx.x * LOOKUP_WARPS + warp;
   if (q >= nq) return;
   const float cx = coords[q * 2], cy = coords[q * 2 + 1];
+  float fa[4], fb[4];   // bilinear fractions and even-column phase of every level: registers of every lane
+  int ph[4];
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const float inv = 1.f / (float)(1 << l);
@@ -151,7 +141,7 @@ __global__ void __launch_bounds__(LOOKUP_WARPS * 32) corr_lookup(CorrLevels lv, 
     const float fx = floorf(x), fy = floorf(y);
     const int x0 = (int)fx - 4, y0 = (int)fy - 4;
     const int xa = x0 & ~1;                       // even column <= x0 (also for negative x0)
-    if (lane == 0) { frac[warp][l][0] = x - fx; frac[warp][l][1] = y - fy; phase[warp][l] = x0 - xa; }
+    fa[l] = x - fx; fb[l] = y - fy; ph[l] = x0 - xa;
     const __half* m = lv.p[l] + q * (long long)(h * w);
     float* T = taps[warp][l];
     if ((w & 1) == 0) {
@@ -177,19 +167,23 @@ __global__ void __launch_bounds__(LOOKUP_WARPS * 32) corr_lookup(CorrLevels lv, 
   }
   __syncwarp();
   __half* o = out + q * out_cs;
-  for (int c = lane; c < out_cs; c += 32) {
-    const unsigned e = otab[c];
-    float val = 0.f;
-    if (e != 0xFFFF) {
-      const int l = e >> 12;
-      const float* T = taps[warp][l] + (e & 0xFFF) + phase[warp][l];
-      const float a = frac[warp][l][0], b = frac[warp][l][1];
-      const float top = T[0] + a * (T[1] - T[0]);
-      const float bot = T[TAP_COLS] + a * (T[TAP_COLS + 1] - T[TAP_COLS]);
-      val = top + b * (bot - top);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const float a = fa[l], b = fb[l];
+    const float* T = taps[warp][l] + ph[l];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int r = lane + 32 * k;                 // output i*9 + j of this level
+      if (r < 81) {
+        const int i = (r * 57) >> 9, j = r - 9 * i;  // r / 9, r % 9 for r < 81
+        const float* t = T + j * TAP_COLS + i;
+        const float top = t[0] + a * (t[1] - t[0]);
+        const float bot = t[TAP_COLS] + a * (t[TAP_COLS + 1] - t[TAP_COLS]);
+        o[l * 81 + r] = __float2half_rn(top + b * (bot - top));
+      }
     }
-    o[c] = __float2half_rn(val);
   }
+  for (int c = 324 + lane; c < out_cs; c += 32) o[c] = __float2half_rn(0.f);   // padding channels
 }
 
 // cnet output -> GRU state: h = tanh(c[:, :128]) into hx[:, 0:128], inp = relu(c[:, 128:]) into hx[:, 128:256]
