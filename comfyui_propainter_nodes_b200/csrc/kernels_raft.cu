@@ -41,15 +41,16 @@ __global__ void instnorm_stats(const __half* __restrict__ x, int HW, int C, floa
 }
 
 // out = [relu]( (x - mean) * rstd );  if residual: out = relu(residual + out)   (ResidualBlock tail)
-__global__ void instnorm_apply(const __half* __restrict__ x, const float* __restrict__ sums,
-                               const __half* __restrict__ residual, __half* __restrict__ out, int HW, int C,
-                               long long total2, int relu) {
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total2) return;
+__global__ void __launch_bounds__(256) instnorm_apply(const __half* __restrict__ x, const float* __restrict__ sums,
+                                                      const __half* __restrict__ residual, __half* __restrict__ out, int HW,
+                                                      int C, int relu) {
+  // grid = (chunks of one image's HW*C/2 channel pairs, images): 32-bit index math, statistics row uniform per block
   const int C2 = C >> 1;
-  const int cp = idx % C2;
-  const long long p = idx / C2;
-  const int n = p / HW;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)(HW * C2)) return;
+  const int n = blockIdx.y;
+  const int cp = i % (unsigned)C2;
+  const long long idx = (long long)n * HW * C2 + i;
   const float inv = 1.f / (float)HW;
   const float* s = sums + (long long)n * 2 * C;
   const float m0 = s[2 * cp] * inv, m1 = s[2 * cp + 1] * inv;
@@ -89,17 +90,18 @@ __global__ void pack_b_operand(const __half* __restrict__ src, __half* __restric
 }
 
 // 2x2 average pooling of every [h][w] correlation map (F.avg_pool2d(corr, 2, stride=2), corr.py:25-27).
-__global__ void corr_pool(const __half* __restrict__ src, __half* __restrict__ dst, long long nq, int h, int w) {
+// One block per query map (32-bit index math); each thread produces output pairs from two 8-byte row reads.
+__global__ void __launch_bounds__(128) corr_pool(const __half* __restrict__ src, __half* __restrict__ dst, int h, int w) {
   const int oh = h >> 1, ow = w >> 1;
-  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= nq * oh * ow) return;
-  const int ox = idx % ow;
-  long long t = idx / ow;
-  const int oy = t % oh;
-  const long long q = t / oh;
-  const __half* s = src + (q * h + 2 * oy) * w + 2 * ox;
-  const float a = __half2float(s[0]) + __half2float(s[1]) + __half2float(s[w]) + __half2float(s[w + 1]);
-  dst[idx] = __float2half_rn(0.25f * a);
+  const long long q = blockIdx.x;
+  const __half* s = src + q * (long long)(h * w);
+  __half* d = dst + q * (long long)(oh * ow);
+  for (int i = threadIdx.x; i < oh * ow; i += blockDim.x) {
+    const int oy = i / ow, ox = i - oy * ow;
+    const __half* r = s + 2 * oy * w + 2 * ox;
+    const float a = __half2float(r[0]) + __half2float(r[1]) + __half2float(r[w]) + __half2float(r[w + 1]);
+    d[i] = __float2half_rn(0.25f * a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -267,8 +269,9 @@ int pp_k_instnorm_stats(const __half* x, int N, int HW, int C, float* sums, cuda
 
 int pp_k_instnorm_apply(const __half* x, const float* sums, const __half* residual, __half* out, int N, int HW, int C,
                         int relu, cudaStream_t st) {
-  const long long total2 = (long long)N * HW * (C / 2);
-  instnorm_apply<<<nblocks(total2), TPB, 0, st>>>(x, sums, residual, out, HW, C, total2, relu);
+  if ((long long)N * HW == 0) return PP_OK;
+  PP_REQUIRE(N <= 65535 && (long long)HW * (C / 2) < (1LL << 31), "instnorm: %d images of %d pixels exceed the grid limits", N, HW);
+  instnorm_apply<<<dim3(pp_ceil_div(HW * (C / 2), 256), N), 256, 0, st>>>(x, sums, residual, out, HW, C, relu);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }
@@ -282,9 +285,9 @@ int pp_k_pack_b_operand(const __half* src, __half* dst, int G, int R, int R_pad,
 }
 
 int pp_k_corr_pool(const __half* src, __half* dst, long long nq, int h, int w, cudaStream_t st) {
-  const long long total = nq * (h / 2) * (w / 2);
-  if (total == 0) return PP_OK;
-  corr_pool<<<nblocks(total), TPB, 0, st>>>(src, dst, nq, h, w);
+  if (nq * (h / 2) * (w / 2) == 0) return PP_OK;
+  PP_REQUIRE(nq < (1LL << 31), "corr_pool: too many query maps");
+  corr_pool<<<(unsigned)nq, 128, 0, st>>>(src, dst, h, w);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }
