@@ -25,6 +25,15 @@ import numpy as np
 import torch
 
 T_FRAMES, HEIGHT, WIDTH = 80, 360, 640
+_OUT_FD = 1
+
+
+def emit(line: str) -> None:
+    """The ONE JSON line of the contract goes to the real stdout; everything else this process or its libraries
+    print on fd 1 (NCCL's version banner, the node's progress lines) is routed to stderr in main()."""
+    os.write(_OUT_FD, (line + "\n").encode())
+
+
 PARAMS = dict(mask_dilates=5, flow_mask_dilates=8, ref_stride=10, neighbor_length=10, subvideo_length=80, raft_iter=20,
               fp16="enable")
 METRIC = "inpainted frames/sec at 640x360, 80-frame subvideo"
@@ -114,7 +123,7 @@ def run_reference(args, rank):
         vals.append(v)
     v = float(np.mean(vals))
     sample = f"first {n} frames of the 80-frame 640x360 clip, raft_iter=20, fp32, CPU oracle port of the reference"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
@@ -281,7 +290,7 @@ def run_b200(args, rank, world):
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"first 3 frames of the same clip and parameters through the CPU oracle ({dt:.1f} s)"}
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -312,6 +321,10 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)      # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)            # ... and send every other write to fd 1 (C libraries included) to stderr
     if args.impl == "reference":
         run_reference(args, rank)
     else:
