@@ -156,3 +156,43 @@ def test_outpaint_tensor_path_matches_pil_path():
         ft1, fm1, md1, orig1 = IU.outpaint_tensors(image, cfg, torch.device("cpu"))
         assert torch.equal(ft0, ft1) and torch.equal(fm0, fm1) and torch.equal(md0, md1)
         assert np.array_equal(np.stack(orig0), orig1.numpy())
+
+
+def test_encoder14_dense_weights_equal_grouped_conv():
+    """gen.encoder.14 (8 groups of 80 -> 32 channels) is registered as a dense conv with block-diagonal weights over
+    cat(x0[256], prev[384]); it must reproduce the reference's grouped conv over the interleaved input
+    (model/propainter.py:268-273)."""
+    import torch.nn.functional as F
+    sd = Wt.synthetic_generator_state_dict()
+    convs, _ = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(), sd)
+    w_dense, b, groups, cmap = convs["gen.encoder.14"]
+    assert groups == 1 and cmap is None and tuple(w_dense.shape[:2]) == (256, 640)
+    g = torch.Generator().manual_seed(11)
+    x0, prev = torch.randn(1, 256, 9, 11, generator=g), torch.randn(1, 384, 9, 11, generator=g)
+    gr = 8
+    # reference: x = cat([x0.view(g, -1), prev.view(g, -1)], 2) per group, then grouped conv
+    xi = torch.cat([x0.view(1, gr, -1, 9, 11), prev.view(1, gr, -1, 9, 11)], 2).view(1, -1, 9, 11)
+    ref = F.conv2d(xi, sd["encoder.layers.14.weight"].float(), sd["encoder.layers.14.bias"].float(), 1, 1, 1, gr)
+    out = F.conv2d(torch.cat([x0, prev], 1), w_dense, b, 1, 1)
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_pad64_layers_are_registered_with_zero_extended_channels():
+    """Layers on the PAD64 list get kernel input channels padded to a multiple of 64 with -1 (zero weight) entries;
+    the activation tensors keep their real channel count (TMA zero-fills the rest, PPConvSeg.cvalid)."""
+    convs, _ = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
+                              Wt.synthetic_generator_state_dict())
+    for name in E.Engine.PAD64_CONVS:
+        w, b, groups, cmap = convs[name]
+        cmap = list(cmap) if cmap is not None else list(range(w.shape[1]))
+        padded = cmap + [-1] * ((-len(cmap)) % 64)
+        assert groups == 1 and len(padded) % 64 == 0 and len(padded) - len(cmap) < 64
+        packed, meta = E.pack_conv_weight(w, 1, padded)
+        assert meta["cin_g"] == len(padded)
+        un = _unpack(packed, meta)[0, : w.shape[0]]                       # [cout, kh*kw*cin_k]
+        un = un[:, : meta["kh"] * meta["kw"] * len(padded)].view(w.shape[0], meta["kh"] * meta["kw"], len(padded))
+        real = [i for i, c in enumerate(padded) if c >= 0]
+        pad = [i for i, c in enumerate(padded) if c < 0]
+        assert float(un[:, :, pad].abs().max()) == 0.0 if pad else True
+        ref = w[:, [padded[i] for i in real]].permute(0, 2, 3, 1).reshape(w.shape[0], -1, len(real)).half().float()
+        assert torch.equal(un[:, :, real], ref)
