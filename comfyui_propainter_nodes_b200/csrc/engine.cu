@@ -116,13 +116,3 @@ int PPConvCall::run(cudaStream_t st) {
   PPProfScope ps(*eng, "conv:" + name, rows, 2.0 * rows * p.Cout_g * p.groups * p.kh * p.kw * p.Cin, 0.0, st);
   return pp_launch_conv(p, st);
 }
-
-int pp_small_conv(PPEngine& e, const std::string& name, const __half* x, int x_cs, int x_co, int C, int cout, void* z,
-                  int z_fp32, void* out, int out_cs, int out_co, int out_fp32, int act_tanh, int N, int H, int W,
-                  cudaStream_t st) {
-  // 3x3 convs with 2-3 output channels run on the TMA halo-tile kernel with a 16-column N tile: the input patch is
-  // read once (no im2col amplification), so they are bound by streaming the input, not by the taps.
-  (void)cout; (void)z; (void)z_fp32;
-  return PPConvCall(e, name, N, H, W).in(x, x_cs, x_co, C).out(out, out_cs, out_co, out_fp32)
-      .act(act_tanh ? PP_ACT_TANH : PP_ACT_NONE).run(st);
-}

@@ -125,13 +125,6 @@ int pp_fuse_upsample();
 
 void pp_build_ring_indices(int nh, int nw, std::vector<int>& out);
 
-// 3x3 conv with <= 3 output channels as a 1x1 tensor-core GEMM producing the 9*cout per-tap partial products
-// (conv "<name>.taps", registered by the packer) followed by the tap gather; bias tensor "<name>.b".
-// `z` is scratch for [N*H*W][32] values (fp32 when z_fp32).
-int pp_small_conv(PPEngine& e, const std::string& name, const __half* x, int x_cs, int x_co, int C, int cout, void* z,
-                  int z_fp32, void* out, int out_cs, int out_co, int out_fp32, int act_tanh, int N, int H, int W,
-                  cudaStream_t st);
-
 // ---- stages ---------------------------------------------------------------------------------------
 int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int iters, float* flows_f, float* flows_b,
                   cudaStream_t st);

@@ -398,8 +398,9 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
     PP_TRY(deconv(e, "gen.decoder.0", encf, n, h4, w4, 128, up, d0, 128, 128, PP_ACT_LRELU, 0.2f, st));
     PP_TRY(PPConvCall(e, "gen.decoder.2", n, h2, w2).in(d0, 128, 0, 128).out(d1, 64, 0).act(PP_ACT_LRELU, 0.2f).run(st));
     PP_TRY(deconv(e, "gen.decoder.4", d1, n, h2, w2, 64, up, d2, 64, 64, PP_ACT_LRELU, 0.2f, st));
-    // 64->3 tail: per-tap partial products (fp16, reuses `up`) + tap gather + tanh
-    PP_TRY(pp_small_conv(e, "gen.decoder.6", d2, 64, 0, 64, 3, up, 0, pred + (size_t)c0 * HWl * 4, 4, 0, 0, 1, n, H, W, st));
+    // 64->3 tail + tanh: halo kernel with a 16-column N tile (the input patch is read once, no im2col amplification)
+    PP_TRY(PPConvCall(e, "gen.decoder.6", n, H, W).in(d2, 64, 0, 64).out(pred + (size_t)c0 * HWl * 4, 4, 0)
+               .act(PP_ACT_TANH).run(st));
   }
   e.arena.release(m2k);
   e.arena.release(mark0);

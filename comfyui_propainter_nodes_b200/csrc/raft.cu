@@ -210,8 +210,6 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
       PP_TRY(pp_alloc(e, &fh, (size_t)M * 256, "flow head"));
       PP_TRY(pp_alloc(e, &coords1, (size_t)M * 2, "coords1"));
       PP_TRY(pp_alloc(e, &delta, (size_t)M * 2, "delta"));
-      float* ztap;
-      PP_TRY(pp_alloc(e, &ztap, (size_t)M * 32, "flow head tap products"));
       for (int si = 0; si < nsub; ++si) {
         const int f1 = subs[si].dir == 0 ? subs[si].b0 : subs[si].b0 + 1;
         PP_TRY(pp_k_cnet_split(cmap + (size_t)f1 * P * 256, hx + (size_t)subs[si].off * P * 384, 384,
@@ -250,7 +248,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
         // FlowHead (update.py:6-14)
         PP_TRY(PPConvCall(e, "raft.update.fh1", B, h8, w8).in(hx, 384, 0, 128).out(fh, 256, 0)
                    .act(PP_ACT_RELU).run(st));
-        PP_TRY(pp_small_conv(e, "raft.update.fh2", fh, 256, 0, 256, 2, ztap, 1, delta, 2, 0, 1, 0, B, h8, w8, st));
+        PP_TRY(PPConvCall(e, "raft.update.fh2", B, h8, w8).in(fh, 256, 0, 256).out(delta, 2, 0, 1).run(st));   // 256 -> 2, fp32 out
         PP_TRY(pp_k_raft_coords_update(delta, coords1, flow8, hx, 384, 382, B, h8, w8, st));
         e.launches++;
       }

@@ -158,13 +158,11 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
   }
   PP_TRY(PPConvCall(e, "rfc.upsample.0", N, h2, w2).in(d1, 32, 0, 32).out(u0, 32, 0).act(PP_ACT_LRELU, 0.2f).run(st));
   if (!fuse) PP_TRY(pp_k_upsample2x(u0, 32, 0, up, 32, 0, N, h2, w2, 32, st));
-  // 32->2 tail: per-tap partial products (fp32 scratch) + tap gather
-  float* ztap;
-  PP_TRY(pp_alloc(e, &ztap, (size_t)N * HW * 32, "rfc tap products"));
+  // 32 -> 2 tail (channels zero-extended to 64 by TMA, 16-column N tile)
   if (fuse) {
     PP_TRY(PPConvCall(e, "rfc.upsample.deconv", N, H, W).in(u0, 32, 0, 32).upsampled2x().out(pred, 2, 0).run(st));
   } else {
-    PP_TRY(pp_small_conv(e, "rfc.upsample.deconv", up, 32, 0, 32, 2, ztap, 1, pred, 2, 0, 0, 0, N, H, W, st));
+    PP_TRY(PPConvCall(e, "rfc.upsample.deconv", N, H, W).in(up, 32, 0, 32).out(pred, 2, 0).run(st));
   }
   e.launches += 3;
 
