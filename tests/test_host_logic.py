@@ -196,3 +196,23 @@ def test_pad64_layers_are_registered_with_zero_extended_channels():
         assert float(un[:, :, pad].abs().max()) == 0.0 if pad else True
         ref = w[:, [padded[i] for i in real]].permute(0, 2, 3, 1).reshape(w.shape[0], -1, len(real)).half().float()
         assert torch.equal(un[:, :, real], ref)
+
+
+def test_bench_reference_arm_prints_one_json_line(monkeypatch, capfd):
+    """bench.py contract: exactly one JSON line on stdout (everything else on stderr) with the agreed keys."""
+    import json
+    import bench
+    monkeypatch.setattr(bench, "cpu_sample", lambda n=3: (0.5, 6.0))
+    monkeypatch.setattr(bench, "_OUT_FD", 1)
+    args = type("A", (), dict(gpus=1, steps=2, warmup=1))()
+    print("noise that must not reach the JSON consumer", file=__import__("sys").stderr)
+    bench.run_reference(args, rank=0)
+    out = capfd.readouterr().out.strip().splitlines()
+    assert len(out) == 1
+    rec = json.loads(out[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in rec, key
+    assert rec["impl"] == "reference" and rec["cpu_baseline"]["kind"] == "port" and rec["e2e"]["h2d_bytes_per_step"] == 0
+    bench.run_reference(args, rank=1)            # other ranks stay silent
+    assert capfd.readouterr().out == ""
