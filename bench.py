@@ -1,13 +1,24 @@
 #!/usr/bin/env python
 """Bench of the ProPainter hot path: inpainted frames/s at 640x360 on an 80-frame subvideo (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode strong|weak]
 
 One "step" = one pass of the whole hot path (RAFT -> flow completion -> image propagation -> sliding-window
-generator -> composite) over one synthetic 80-frame 640x360 clip per GPU.  `value` is measured with the
-prepared tensors already resident in HBM; `e2e` goes through the ComfyUI node call with host tensors (host
-pre-processing, H2D, D2H of the result inside the timed region).  Weights are seeded synthetic checkpoints of
-the real architectures (no network in this environment).
+generator -> composite) over one synthetic 80-frame 640x360 clip.  `value` is measured with the prepared tensors
+already resident in HBM; `e2e` goes through the ComfyUI node call with pageable host tensors (pre-processing, H2D and
+the D2H of the result inside the timed region).  Weights are seeded synthetic checkpoints of the real architectures
+(no network in this environment).
+
+N > 1 (torchrun, one rank per GPU): the default is north_star's split -- ONE 80-frame subvideo shared by all N GPUs
+(`scaling: "strong"`): RAFT pairs, the per-frame parts of flow completion and the sliding windows are sharded, the
+exchange steps are NCCL all-gathers over NVLink; BASELINE config[2] (240 frames, subvideo_length 80, same sharding) is
+reported alongside as `config2_240f`.  `--mode weak` runs one independent subvideo per GPU instead.
+
+`--impl reference` times the UNMODIFIED reference (installed by __graft_entry__.build() into baseline/_ref, which is
+git-ignored but travels to the GPU box) on the host cores: one pass over the first 16 frames of the same clip, all
+threads; it also reports the reference's own PyTorch-CUDA fp16 path on the same B200 at the full 80 frames
+(`reference_cuda`, the number SURVEY.md 8d calls "the number to beat").  Without baseline/_ref it falls back to the
+CPU oracle port.
 """
 import argparse
 import contextlib
@@ -15,8 +26,10 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -25,6 +38,7 @@ import numpy as np
 import torch
 
 T_FRAMES, HEIGHT, WIDTH = 80, 360, 640
+T_CONFIG2 = 240
 _OUT_FD = 1
 
 
@@ -37,7 +51,8 @@ def emit(line: str) -> None:
 PARAMS = dict(mask_dilates=5, flow_mask_dilates=8, ref_stride=10, neighbor_length=10, subvideo_length=80, raft_iter=20,
               fp16="enable")
 METRIC = "inpainted frames/sec at 640x360, 80-frame subvideo"
-WORKLOAD = "configs[1]: 80-frame 640x360 synthetic clip, ref_stride=10 neighbor_length=10 raft_iter=20 fp16, 1 clip per B200"
+WORKLOAD = "configs[1]: 80-frame 640x360 synthetic clip, ref_stride=10 neighbor_length=10 raft_iter=20 fp16"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def peaks():
@@ -47,6 +62,13 @@ def peaks():
         return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     source="measured")
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, source="fallback")
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernels from the committed ncu pass (tools/ncu_traffic.py ->
+    profiles/traffic.json); None when no capture of the current kernels is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 class ClockSampler(threading.Thread):
@@ -77,59 +99,157 @@ class ClockSampler(threading.Thread):
                     samples=len(sm))
 
 
-def synthetic_inputs():
+def synthetic_inputs(T=T_FRAMES):
     from comfyui_propainter_nodes_b200.synthetic import synthetic_clip, synthetic_mask
-    return synthetic_clip(T_FRAMES, HEIGHT, WIDTH, 1234), synthetic_mask(T_FRAMES, HEIGHT, WIDTH)
+    return synthetic_clip(T, HEIGHT, WIDTH, 1234), synthetic_mask(T, HEIGHT, WIDTH)
 
 
-# ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (the reference itself is a Python package that cannot travel to the GPU box)
-# ------------------------------------------------------------------------------------------------------------------
-def cpu_threads():
-    """Host threads for the CPU arm: all cores up to 16 (beyond that the small 1/8-res convs of the recurrent
-    stages get slower with more threads on the 128-core host; measured in profiles/)."""
-    return min(os.cpu_count() or 1, int(os.environ.get("PP_CPU_THREADS", 16)))
-
-
-def cpu_sample(n_frames=3):
-    """Times the CPU oracle on a bounded sample of the same workload: the first `n_frames` frames of the clip with
-    the workload's parameters.  Returns (frames/s, seconds)."""
+def synthetic_state_dicts():
     from comfyui_propainter_nodes_b200 import weights as Wt
+    return Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(), Wt.synthetic_generator_state_dict()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference itself (baseline/_ref) and, when it is absent, the CPU oracle port
+# ------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads of the CPU arm: every host core up to PP_CPU_THREADS (default 32 -- beyond that the 1/8-resolution
+    convolutions of the recurrent stages stop scaling on the 128-core host, profiles/r01_cpu_threads.log)."""
+    return min(os.cpu_count() or 1, int(os.environ.get("PP_CPU_THREADS", 32)))
+
+
+def load_reference():
+    """Import the unmodified reference package from baseline/_ref with a stub ``comfy.model_management`` (the one
+    ComfyUI module it imports).  Returns the package's modules or None when it was not installed."""
+    pkg = os.path.join(REF_DIR, "comfyui_propainter_nodes")
+    if not os.path.exists(os.path.join(pkg, "propainter_inference.py")):
+        return None
+    sys.dont_write_bytecode = True
+    if "comfy" not in sys.modules:
+        comfy, mm = types.ModuleType("comfy"), types.ModuleType("comfy.model_management")
+        mm.get_torch_device = lambda: torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        comfy.model_management = mm
+        sys.modules["comfy"], sys.modules["comfy.model_management"] = comfy, mm
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import importlib
+    ns = types.SimpleNamespace()
+    ns.RI = importlib.import_module("comfyui_propainter_nodes.propainter_inference")
+    ns.RU = importlib.import_module("comfyui_propainter_nodes.utils.image_utils")
+    ns.MU = importlib.import_module("comfyui_propainter_nodes.utils.model_utils")
+    ns.RAFT_bi = importlib.import_module("comfyui_propainter_nodes.model.modules.flow_comp_raft").RAFT_bi
+    ns.RFC = importlib.import_module("comfyui_propainter_nodes.model.recurrent_flow_completion").RecurrentFlowCompleteNet
+    ns.GEN = importlib.import_module("comfyui_propainter_nodes.model.propainter").InpaintGenerator
+    return ns
+
+
+def reference_models(ref, device, use_half):
+    """What the reference's initialize_models builds (utils/model_utils.py:49-59), from the synthetic checkpoints
+    instead of the downloaded files."""
+    raft_sd, rfc_sd, gen_sd = synthetic_state_dicts()
+    path = os.path.join(tempfile.mkdtemp(), "raft-things.pth")
+    torch.save(raft_sd, path)
+    with contextlib.redirect_stdout(sys.stderr):
+        raft = ref.RAFT_bi(path, device)
+        rfc = ref.RFC()
+        rfc.load_state_dict(rfc_sd, strict=True)
+        for p in rfc.parameters():
+            p.requires_grad = False
+        rfc.to(device).eval()
+        gen = ref.GEN()
+        gen.load_state_dict(gen_sd, strict=True)
+        gen.to(device).eval()
+    if use_half == "enable":
+        rfc, gen = rfc.half(), gen.half()
+    return ref.MU.Models(raft, rfc, gen)
+
+
+def reference_pass(ref, models, image, mask, device, fp16):
+    """The reference's own hot path on one clip: process_inpainting + feature_propagation, timed by
+    wall clock with the device synchronised.  Returns (frames/s, seconds)."""
+    T = image.shape[0]
+    icfg = ref.RU.ImageConfig(WIDTH, HEIGHT, PARAMS["mask_dilates"], PARAMS["flow_mask_dilates"], (WIDTH, HEIGHT), T)
+    ft, fm, md, orig = ref.RU.prepare_frames_and_masks(ref.RU.convert_image_to_frames(image), mask, icfg, device)
+    cfg = ref.RI.ProPainterConfig(PARAMS["ref_stride"], PARAMS["neighbor_length"], PARAMS["subvideo_length"],
+                                  PARAMS["raft_iter"], fp16, T, device, icfg.process_size)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(sys.stderr), contextlib.redirect_stderr(open(os.devnull, "w")):
+        uf, um, pf = ref.RI.process_inpainting(models, ft, fm, md, cfg)
+        ref.RI.feature_propagation(models.inpaint_model, uf, um, md, pf, orig, cfg)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return T / dt, dt
+
+
+def oracle_pass(n_frames):
+    """CPU oracle port on the first `n_frames` frames of the clip (only used when baseline/_ref is absent)."""
     from comfyui_propainter_nodes_b200.utils import image_utils as IU
     from oracle import propainter_oracle as O
     image, mask = synthetic_inputs()
     image, mask = image[:n_frames], mask[:n_frames]
     icfg = IU.ImageConfig(WIDTH, HEIGHT, PARAMS["mask_dilates"], PARAMS["flow_mask_dilates"], (WIDTH, HEIGHT), n_frames)
     ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(image), mask, icfg, torch.device("cpu"))
-    sds = (Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(), Wt.synthetic_generator_state_dict())
     t0 = time.perf_counter()
-    O.run_pipeline(*sds, ft, fm, md, orig, raft_iter=PARAMS["raft_iter"], subvideo_length=PARAMS["subvideo_length"],
-                   neighbor_length=PARAMS["neighbor_length"], ref_stride=PARAMS["ref_stride"])
+    O.run_pipeline(*synthetic_state_dicts(), ft, fm, md, orig, raft_iter=PARAMS["raft_iter"],
+                   subvideo_length=PARAMS["subvideo_length"], neighbor_length=PARAMS["neighbor_length"],
+                   ref_stride=PARAMS["ref_stride"])
     dt = time.perf_counter() - t0
     return n_frames / dt, dt
+
+
+def cpu_sample(n_frames):
+    """(frames/s, seconds, kind) of the CPU baseline on the first n_frames frames: the real reference when installed,
+    else the oracle port."""
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    ref = load_reference()
+    if ref is None:
+        v, dt = oracle_pass(n_frames)
+        return v, dt, "port", cores
+    image, mask = synthetic_inputs()
+    models = reference_models(ref, torch.device("cpu"), "disable")
+    v, dt = reference_pass(ref, models, image[:n_frames], mask[:n_frames], torch.device("cpu"), "disable")
+    return v, dt, "reference", cores
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = cpu_threads()
-    torch.set_num_threads(cores)
-    n = 3
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(n)
-    vals = []
-    for _ in range(args.steps):
-        v, _ = cpu_sample(n)
-        vals.append(v)
-    v = float(np.mean(vals))
-    sample = f"first {n} frames of the 80-frame 640x360 clip, raft_iter=20, fp32, CPU oracle port of the reference"
-    emit(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+    n = int(os.environ.get("PP_REF_FRAMES", 16))
+    if args.warmup > 0:
+        cpu_sample(3)            # thread pools, allocator and first-touch of the weights
+    v, dt, kind, cores = cpu_sample(n)
+    what = "the unmodified reference (baseline/_ref), fp32, PyTorch CPU" if kind == "reference" else "CPU oracle port of the reference, fp32"
+    sample = (f"ONE pass over the first {n} frames of the 80-frame 640x360 clip (raft_iter=20, all other parameters of the "
+              f"workload), {what}, {cores} threads, {dt:.1f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": 1,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * dt, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD + " (CPU arm: first %d frames)" % n},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+        "note": "timed once (a 16-frame pass is tens of seconds); --steps/--warmup of the command line are not repeated",
+    }
+    # second stated baseline: the reference's own PyTorch-CUDA fp16 path on this B200 at the full workload
+    if kind == "reference" and torch.cuda.is_available() and not args.no_ref_cuda:
+        try:
+            ref = load_reference()
+            dev = torch.device("cuda", 0)
+            models = reference_models(ref, dev, PARAMS["fp16"])
+            image, mask = synthetic_inputs()
+            reference_pass(ref, models, image[:20], mask[:20], dev, PARAMS["fp16"])   # warm-up (cuDNN autotune, allocator)
+            vals = [reference_pass(ref, models, image, mask, dev, PARAMS["fp16"]) for _ in range(2)]
+            best = max(vals)
+            line["reference_cuda"] = {"value": best[0], "unit": "frames/s", "seconds": best[1], "frames": T_FRAMES,
+                                      "what": "unmodified reference, PyTorch eager CUDA, fp16=enable, same 80-frame clip and weights, best of 2 after warm-up, "
+                                              "process_inpainting + feature_propagation (inputs resident on the device)",
+                                      "torch": torch.__version__, "gpu": torch.cuda.get_device_name(0)}
+        except Exception as ex:  # the CPU number above stands on its own
+            line["reference_cuda"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -137,40 +257,47 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world):
     import torch.distributed as dist
-    from comfyui_propainter_nodes_b200 import weights as Wt
     from comfyui_propainter_nodes_b200 import propainter_inference as PI
     from comfyui_propainter_nodes_b200.propainter_nodes import ProPainterInpaint, _to_host
     from comfyui_propainter_nodes_b200.utils import image_utils as IU
     from comfyui_propainter_nodes_b200.utils import model_utils as MU
+    from comfyui_propainter_nodes_b200 import parallel as PAR
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    models = MU.build_models(dev, Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
-                             Wt.synthetic_generator_state_dict(), workspace_gb=64.0)
-    MU._CACHE[str(dev)] = models          # the node's initialize_models() finds the resident engine
+    models = MU.build_models(dev, *synthetic_state_dicts())      # arena sized per clip (the node path)
+    MU.set_resident_models(dev, models)                           # the node's initialize_models() returns this engine
     eng = models.raft_model.engine
-    image, mask = synthetic_inputs()      # every rank processes its own (identical) 80-frame subvideo: weak scaling
-    icfg = IU.ImageConfig(WIDTH, HEIGHT, PARAMS["mask_dilates"], PARAMS["flow_mask_dilates"], (WIDTH, HEIGHT), T_FRAMES)
-    ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(image), mask, icfg, dev)
-    orig_dev = torch.from_numpy(np.stack(orig)).to(dev)
-    cfg = PI.ProPainterConfig(PARAMS["ref_stride"], PARAMS["neighbor_length"], PARAMS["subvideo_length"],
-                              PARAMS["raft_iter"], PARAMS["fp16"], T_FRAMES, dev, icfg.process_size)
+    strong = world > 1 and args.mode == "strong"
+    if world > 1:
+        PAR.init_engine_comm(eng)        # NCCL communicator inside the C library (pp_comm_init), id broadcast via torch
+
+    def prepared(T):
+        image, mask = synthetic_inputs(T)
+        icfg = IU.ImageConfig(WIDTH, HEIGHT, PARAMS["mask_dilates"], PARAMS["flow_mask_dilates"], (WIDTH, HEIGHT), T)
+        ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(image), mask, icfg, dev)
+        cfg = PI.ProPainterConfig(PARAMS["ref_stride"], PARAMS["neighbor_length"], PARAMS["subvideo_length"],
+                                  PARAMS["raft_iter"], PARAMS["fp16"], T, dev, icfg.process_size)
+        return image, mask, ft, fm, md, torch.from_numpy(np.stack(orig)).to(dev), cfg
+
+    image, mask, ft, fm, md, orig_dev, cfg = prepared(T_FRAMES)
+    eng.reserve_for_clip(T_FRAMES, HEIGHT, WIDTH)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
 
-    strong = args.mode == "strong" and world > 1
-
-    def step():
+    def run_clip(ft, fm, md, orig_dev, cfg):
         if strong:
-            from comfyui_propainter_nodes_b200.parallel import inpaint_clip_distributed
-            return inpaint_clip_distributed(models, ft, fm, md, orig_dev, cfg)
+            return PAR.inpaint_clip_distributed(models, ft, fm, md, orig_dev, cfg)
         uf, um, flows = PI.process_inpainting(models, ft, fm, md, cfg)
         return PI.feature_propagation_device(models.inpaint_model, uf, um, md, flows, orig_dev, cfg)
 
+    def step():
+        return run_clip(ft, fm, md, orig_dev, cfg)
+
     def staged():
-        """Same work as step(), with CUDA events between the stages (reported as stage_ms)."""
+        """Same work as step() on one GPU, with CUDA events between the stages (reported as stage_ms)."""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
         gt = PI.compute_flow(models.raft_model, ft, cfg)
@@ -190,45 +317,47 @@ def run_b200(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launch stream, L2 flushed in between; max over ranks."""
+        barrier()
+        times = []
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        barrier()
+        total = torch.tensor([sum(times)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item()) / steps
+
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
     l0 = eng.launch_count
-    times = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = step()
-        b.record()
-        torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
+    ms_per_step = timed(step, args.steps)
     launches = (eng.launch_count - l0) // max(args.steps, 1)
-    barrier()
-    total_ms = torch.tensor([sum(times)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(total_ms.item()) / args.steps
-    value = (1 if strong else world) * T_FRAMES / (ms_per_step / 1000.0)
+    clips = 1 if (strong or world == 1) else world
+    value = clips * T_FRAMES / (ms_per_step / 1000.0)
 
-    # ---- end to end through the node API with host tensors (pre-processing + H2D + D2H inside)
+    # ---- end to end through the node API with (pageable) host tensors: pre-processing + H2D + D2H inside
     node = ProPainterInpaint()
-    img_host, mask_host = image.pin_memory(), mask.pin_memory()
+
     def e2e_step():
         if strong:   # host tensors -> device pre-processing -> sharded clip -> float IMAGE back on the host
-            from comfyui_propainter_nodes_b200.parallel import inpaint_clip_distributed
-            f, m1, m2, o = eng.preprocess(img_host, mask_host, PARAMS["flow_mask_dilates"], PARAMS["mask_dilates"])
-            return _to_host(eng.postprocess(inpaint_clip_distributed(models, f, m1, m2, o, cfg)))
+            f, m1, m2, o = eng.preprocess(image, mask, PARAMS["flow_mask_dilates"], PARAMS["mask_dilates"])
+            return _to_host(eng.postprocess(PAR.inpaint_clip_distributed(models, f, m1, m2, o, cfg)))
         with contextlib.redirect_stdout(sys.stderr):   # the node prints progress; stdout carries only the JSON line
-            frames, _, _ = node.propainter_inpainting(img_host, mask_host, WIDTH, HEIGHT, **PARAMS)
+            frames, _, _ = node.propainter_inpainting(image, mask, WIDTH, HEIGHT, **PARAMS)
         return frames
     e2e_value = None
     if not args.no_e2e:
-        # two warm-up calls whose results are held the way a caller (ComfyUI's output cache) holds them: the IMAGE
-        # result lives in page-locked blocks of torch's caching host allocator, and the steady state alternates
-        # between two blocks (the previous result is released only after the next one exists)
+        # two warm-up calls whose results are held the way a caller (ComfyUI's output cache) holds them
         res = e2e_step()
         res = e2e_step()
         barrier()
@@ -240,19 +369,34 @@ def run_b200(args, rank, world):
         e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e_value = (1 if strong else world) * T_FRAMES / float(e2e_s.item())
+        e2e_value = clips * T_FRAMES / float(e2e_s.item())
+        del res
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    h2d = img_host.numel() * 4 + mask_host.numel() * 4      # the node uploads the IMAGE / MASK float tensors
+    h2d = image.numel() * 4 + mask.numel() * 4              # the node uploads the IMAGE / MASK float tensors
     d2h = T_FRAMES * HEIGHT * WIDTH * 3 * 4                  # and downloads the float32 IMAGE result
+
+    # ---- BASELINE config[2]: 240 frames, subvideo_length 80 (3 sub-video chunks), same sharding
+    c2 = None
+    if not args.no_config2:
+        _, _, ft2, fm2, md2, orig2, cfg2 = prepared(T_CONFIG2)
+        eng.reserve_for_clip(T_CONFIG2, HEIGHT, WIDTH)
+        fn2 = lambda: run_clip(ft2, fm2, md2, orig2, cfg2)
+        fn2()
+        ms2 = timed(fn2, 2)
+        c2 = {"workload": "configs[2]: 240-frame 640x360 clip, subvideo_length=80", "frames": T_CONFIG2, "steps": 2,
+              "ms_per_step": ms2, "value": clips * T_CONFIG2 / (ms2 / 1000.0), "unit": "frames/s"}
+        del ft2, fm2, md2, orig2
 
     # ---- per-kernel timing of one extra step (CUDA events on the launch stream) for the roofline
     roof, extra, stage_ms = None, [], None
     if strong and not args.no_profile and rank != 0:
         step()                      # the profiled step below is collective in strong mode
     if rank == 0 and not args.no_profile:
-        stage_ms = staged()
+        if world == 1:
+            stage_ms = staged()
         pk = peaks()
+        traffic = ncu_traffic()
         eng.profile_enable(True)
         step()
         prof = eng.profile_dump()
@@ -260,21 +404,28 @@ def run_b200(args, rank, world):
         conv = {k: v for k, v in prof.items() if k.startswith("conv:")}
         conv_ms = sum(v["ms"] for v in conv.values())
         conv_fl = sum(v["flops"] for v in conv.values())
+        n_conv = sum(v["count"] for v in conv.values())
         all_ms = sum(v["ms"] for v in prof.values())
         ach = conv_fl / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_igemm_kernel (tcgen05 convolutions: TMA halo-tile kernel for stride-1 convs and linears, cp.async implicit GEMM for the rest), aggregate over all conv launches of the step",
+        roof = {"bound": "tensor", "kernel": "conv_halo_kernel + conv_igemm_kernel (tcgen05 convolutions / linears), aggregate over all conv launches of the step; "
+                                             "flops are ALGORITHMIC: 2 x output pixels x Cout x kh x kw x Cin/groups of the reference layer (no padded channels, no block-diagonal zeros)",
                 "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                "traffic": None, "peak_source": pk["source"] + " bf16 sustained", "share_of_profiled_step": conv_ms / all_ms if all_ms else None,
-                "launches": sum(v["count"] for v in conv.values())}
-        for name in ("corr_lookup", "imgprop_step", "dcn_sample", "featprop_warp", "fold_ffn"):
+                "traffic": traffic.get("conv_bytes_per_launch"), "traffic_note": traffic.get("note"),
+                "peak_source": pk["source"] + " bf16 sustained", "share_of_profiled_step": conv_ms / all_ms if all_ms else None,
+                "launches": n_conv, "flops_per_launch": conv_fl / max(n_conv, 1), "ms_per_launch": conv_ms / max(n_conv, 1)}
+        for name in ("corr_lookup", "imgprop", "dcn_sample", "featprop_warp", "fold_ffn"):
             if name in prof and prof[name]["ms"] > 0:
                 v = prof[name]
                 gbs = v["bytes"] / (v["ms"] / 1e3) / 1e9
                 extra.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                              "frac": gbs / pk["hbm"], "launches": v["count"], "ms": v["ms"]})
+                              "frac": gbs / pk["hbm"], "launches": v["count"], "ms": v["ms"],
+                              "traffic": traffic.get(name + "_bytes_per_launch")})
         if "attention" in prof:
             v = prof["attention"]
-            extra.append({"kernel": "window_attention_tc (tcgen05) + window_attention (mma.sync, unmasked windows); flops are an upper bound (all windows masked)", "bound": "tensor",
+            tf = v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 else 0.0
+            extra.append({"kernel": "window_attention_tc (tcgen05, masked windows) + window_attention (unmasked windows)", "bound": "tensor",
+                          "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
+                          "flops": "4 x queries x keys x 128 per head of the windows that are actually masked / unmasked in this clip",
                           "ms": v["ms"], "launches": v["count"]})
         if args.profile_out:
             with open(args.profile_out, "w") as fh:
@@ -284,25 +435,33 @@ def run_b200(args, rank, world):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = cpu_threads()
-        torch.set_num_threads(cores)
-        v, dt = cpu_sample(3)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"first 3 frames of the same clip and parameters through the CPU oracle ({dt:.1f} s)"}
+        v, dt, kind, cores = cpu_sample(4)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": f"first 4 frames of the same clip and parameters ({'unmodified reference from baseline/_ref' if kind == 'reference' else 'CPU oracle port'}, fp32, {dt:.1f} s)"}
     if rank == 0:
+        if strong:
+            par = (f"ONE subvideo sharded over {world} GPUs: RAFT pairs, flow-completion encoder/decoder frames and direction passes, "
+                   f"generator windows; NCCL all-gathers of flows / features / predictions (pp_comm_*)")
+        elif world > 1:
+            par = f"{world} independent subvideos, no data-path collective"
+        else:
+            par = "single GPU"
         emit(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if (world > 1 and not strong) else "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": T_FRAMES / world if strong else T_FRAMES, "l2": "flushed between steps (256 MiB write)",
-                       "weights": "seeded synthetic checkpoints", "parallelism": (f"1 subvideo sharded over {world} GPUs (RAFT pairs + windows, 2 all-gathers)" if strong
-                                       else f"{world} independent subvideos, no data-path collective"),
+            "config": {"workload": WORKLOAD + (", ONE clip shared by all GPUs" if strong else ", 1 clip per B200"),
+                       "frames_per_gpu": T_FRAMES / world if strong else T_FRAMES, "l2": "flushed between steps (256 MiB write)",
+                       "weights": "seeded synthetic checkpoints", "parallelism": par,
+                       "e2e_inputs": "pageable host tensors (what ComfyUI hands a node); result in a pinned block of torch's caching host allocator",
                        "roofline_timing": "one extra profiled step after the timed region"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "roofline_other": extra,
-            "stage_ms": stage_ms, "cpu_baseline": cpu, "workspace_peak_gb": eng.workspace_peak / 2 ** 30,
+            "stage_ms": stage_ms, "config2_240f": c2, "cpu_baseline": cpu, "workspace_peak_gb": eng.workspace_peak / 2 ** 30,
         }))
     if world > 1:
+        PAR.destroy_engine_comm(eng)
         dist.destroy_process_group()
 
 
@@ -312,11 +471,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = one 80-frame subvideo per GPU (default); strong = ONE subvideo shared by all GPUs")
+    ap.add_argument("--mode", default="strong", choices=["strong", "weak"],
+                    help="N>1: strong = ONE 80-frame subvideo shared by all GPUs (default, north_star); weak = one subvideo per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true", help="skip the node-level end-to-end leg (profiling runs)")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel timed extra step")
+    ap.add_argument("--no-config2", action="store_true", help="skip the 240-frame config[2] leg")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="reference arm: skip the reference's PyTorch-CUDA leg")
     ap.add_argument("--profile-out", default=None, help="write the full per-kernel table (JSON) here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -4,18 +4,45 @@
 #include "../../include/propainter_b200.h"
 #include "engine.cuh"
 
+// Makes the engine's device current for the duration of one API call and restores the caller's device afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false, ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      ok = cudaSetDevice(dev) == cudaSuccess;
+      changed = ok;
+    }
+  }
+  ~DeviceGuard() {
+    if (changed && prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 #define PP_HANDLE(h)                                     \
   if ((h) == nullptr) {                                  \
     pp_set_error("null engine handle");                  \
     return PP_ERR_ARG;                                   \
   }                                                      \
   PPEngine& e = *reinterpret_cast<PPEngine*>(h);         \
-  if (cudaSetDevice(e.device) != cudaSuccess) {          \
+  DeviceGuard _dev_guard(e.device);                      \
+  if (!_dev_guard.ok) {                                  \
     pp_set_error("cudaSetDevice(%d) failed", e.device);  \
     return PP_ERR_CUDA;                                  \
   }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Restores the arena to its state at entry on EVERY exit of a stage call (error paths included): a failed call
+// ("workspace exhausted", bad argument after a partial allocation) must not shrink the workspace of the cached engine.
+struct ArenaGuard {
+  PPArena& a;
+  size_t m;
+  bool keep = false;
+  explicit ArenaGuard(PPArena& arena) : a(arena), m(arena.mark()) {}
+  ~ArenaGuard() { if (!keep) a.release(m); }
+};
 
 extern "C" {
 
@@ -38,9 +65,47 @@ int pp_create(int device, void* workspace, size_t workspace_bytes, pp_handle* ou
   return PP_OK;
 }
 
-int pp_destroy(pp_handle h) {
-  if (h != nullptr) delete reinterpret_cast<PPEngine*>(h);
+int pp_set_workspace(pp_handle h, void* workspace, size_t workspace_bytes) {
+  PP_HANDLE(h);
+  PP_REQUIRE(!e.gen.active, "pp_set_workspace: a generator session is active (call pp_gen_end first)");
+  PP_REQUIRE(e.arena.off == 0, "pp_set_workspace: the arena is in use");
+  PP_REQUIRE(workspace != nullptr && workspace_bytes >= (64u << 20), "pp_set_workspace: workspace must be >= 64 MiB");
+  PP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pp_set_workspace: workspace must be 256-byte aligned");
+  e.arena.base = static_cast<uint8_t*>(workspace);
+  e.arena.cap = workspace_bytes;
+  e.arena.peak = 0;
   return PP_OK;
+}
+
+int pp_destroy(pp_handle h) {
+  if (h != nullptr) {
+    pp_comm_destroy_impl(*reinterpret_cast<PPEngine*>(h));
+    delete reinterpret_cast<PPEngine*>(h);
+  }
+  return PP_OK;
+}
+
+int pp_comm_unique_id(void* out128) {
+  PP_REQUIRE(out128 != nullptr, "pp_comm_unique_id: null pointer");
+  return pp_comm_unique_id_impl(out128);
+}
+
+int pp_comm_init(pp_handle h, const void* unique_id128, int rank, int world) {
+  PP_HANDLE(h);
+  PP_REQUIRE(unique_id128 != nullptr, "pp_comm_init: null id");
+  return pp_comm_init_impl(e, unique_id128, rank, world);
+}
+
+int pp_comm_destroy(pp_handle h) {
+  PP_HANDLE(h);
+  return pp_comm_destroy_impl(e);
+}
+
+int pp_comm_all_gather_rows(pp_handle h, void* buf, const long long* rows_per_member, size_t row_bytes, int first_rank,
+                            int n_members, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(buf != nullptr && rows_per_member != nullptr && row_bytes > 0, "pp_comm_all_gather_rows: bad argument");
+  return pp_comm_all_gather_rows_impl(e, buf, rows_per_member, row_bytes, first_rank, n_members, as_stream(stream));
 }
 
 int pp_register_conv(pp_handle h, const char* name, const void* w, const float* bias, int cout_g, int cout_g_pad,
@@ -57,6 +122,15 @@ int pp_register_conv(pp_handle h, const char* name, const void* w, const float* 
   return PP_OK;
 }
 
+int pp_set_conv_macs(pp_handle h, const char* name, double macs_per_pixel) {
+  PP_HANDLE(h);
+  PP_REQUIRE(name != nullptr, "pp_set_conv_macs: null name");
+  auto it = e.convs.find(name);
+  PP_REQUIRE(it != e.convs.end(), "pp_set_conv_macs: conv '%s' is not registered", name);
+  it->second.macs_per_pixel = macs_per_pixel;
+  return PP_OK;
+}
+
 int pp_register_tensor(pp_handle h, const char* name, const void* ptr, size_t bytes) {
   PP_HANDLE(h);
   PP_REQUIRE(name != nullptr && ptr != nullptr, "pp_register_tensor: null argument");
@@ -70,6 +144,7 @@ int pp_raft_bidir(pp_handle h, const float* frames, int T, int H, int W, int ite
                   void* stream) {
   PP_HANDLE(h);
   PP_REQUIRE(frames && flows_f && flows_b, "pp_raft_bidir: null pointer");
+  ArenaGuard guard(e.arena);
   return pp_stage_raft(e, frames, T, H, W, iters, flows_f, flows_b, as_stream(stream));
 }
 
@@ -77,6 +152,7 @@ int pp_flow_complete(pp_handle h, const float* flows_f, const float* flows_b, co
                      int W, float* out_f, float* out_b, void* stream) {
   PP_HANDLE(h);
   PP_REQUIRE(flows_f && flows_b && flow_masks && out_f && out_b, "pp_flow_complete: null pointer");
+  ArenaGuard guard(e.arena);
   return pp_stage_flow_complete(e, flows_f, flows_b, flow_masks, T, H, W, out_f, out_b, as_stream(stream));
 }
 
@@ -86,20 +162,31 @@ int pp_image_propagate(pp_handle h, const float* frames, const float* masks, con
   PP_HANDLE(h);
   PP_REQUIRE(frames && masks && flows_f && flows_b && updated_frames && updated_masks,
              "pp_image_propagate: null pointer");
+  ArenaGuard guard(e.arena);
   return pp_stage_image_propagate(e, frames, masks, flows_f, flows_b, T, H, W, updated_frames, updated_masks,
                                   as_stream(stream));
 }
 
-int pp_gen_begin(pp_handle h, const float* updated_frames, const float* masks_dilated, const float* updated_masks,
-                 const float* flows_f, const float* flows_b, int T, int H, int W, void* stream) {
+int pp_gen_begin_subset(pp_handle h, const float* updated_frames, const float* masks_dilated,
+                        const float* updated_masks, const float* flows_f, const float* flows_b, int T, int H, int W,
+                        const unsigned char* frames_needed, void* stream) {
   PP_HANDLE(h);
   PP_REQUIRE(updated_frames && masks_dilated && updated_masks && flows_f && flows_b, "pp_gen_begin: null pointer");
-  return pp_stage_gen_begin(e, updated_frames, masks_dilated, updated_masks, flows_f, flows_b, T, H, W, as_stream(stream));
+  const int r = pp_stage_gen_begin(e, updated_frames, masks_dilated, updated_masks, flows_f, flows_b, T, H, W,
+                                   frames_needed, as_stream(stream));
+  if (r != PP_OK) pp_stage_gen_end(e);   // a failed begin leaves no session and no allocation behind
+  return r;
+}
+
+int pp_gen_begin(pp_handle h, const float* updated_frames, const float* masks_dilated, const float* updated_masks,
+                 const float* flows_f, const float* flows_b, int T, int H, int W, void* stream) {
+  return pp_gen_begin_subset(h, updated_frames, masks_dilated, updated_masks, flows_f, flows_b, T, H, W, nullptr, stream);
 }
 
 int pp_gen_window(pp_handle h, const int* frame_ids, int t, int l_t, void* pred_f16, void* stream) {
   PP_HANDLE(h);
   PP_REQUIRE(frame_ids && pred_f16, "pp_gen_window: null pointer");
+  ArenaGuard guard(e.arena);
   return pp_stage_gen_window(e, frame_ids, t, l_t, static_cast<__half*>(pred_f16), as_stream(stream));
 }
 
@@ -107,6 +194,7 @@ int pp_gen_run(pp_handle h, const int* frame_ids, const int* win_t, const int* w
                void* stream) {
   PP_HANDLE(h);
   PP_REQUIRE(frame_ids && win_t && win_lt && pred_f16, "pp_gen_run: null pointer");
+  ArenaGuard guard(e.arena);
   return pp_stage_gen_run(e, frame_ids, win_t, win_lt, n_windows, static_cast<__half*>(pred_f16), as_stream(stream));
 }
 
@@ -116,12 +204,13 @@ int pp_gen_end(pp_handle h) {
 }
 
 int pp_composite(pp_handle h, const void* pred_f16, const float* masks_dilated, const uint8_t* orig, uint8_t* comp,
-                 const int* frame_ids_dev, const int* first_visit_dev, int l_t, int H, int W, void* stream) {
+                 const int* frame_ids_dev, const int* first_visit_dev, int l_t, int H, int W, int half_math,
+                 void* stream) {
   PP_HANDLE(h);
   PP_REQUIRE(pred_f16 && masks_dilated && orig && comp && frame_ids_dev && first_visit_dev, "pp_composite: null pointer");
   e.launches++;
   return pp_k_composite(static_cast<const __half*>(pred_f16), 4, masks_dilated, orig, comp, frame_ids_dev,
-                        first_visit_dev, l_t, H, W, as_stream(stream));
+                        first_visit_dev, l_t, H, W, half_math, as_stream(stream));
 }
 
 int pp_preprocess(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
@@ -129,14 +218,13 @@ int pp_preprocess(pp_handle h, const float* image, const float* mask, int mask_f
                   float* masks_dilated, void* stream) {
   PP_HANDLE(h);
   PP_REQUIRE(image && mask && orig_u8 && frames && flow_masks && masks_dilated, "pp_preprocess: null pointer");
-  const size_t mark = e.arena.mark();
+  ArenaGuard guard(e.arena);
   uint8_t* scratch;
   PP_TRY(pp_alloc(e, &scratch, (size_t)mask_frames * H * W, "mask scratch"));
   PP_TRY(pp_k_quantize_frames(image, orig_u8, frames, T, H, W, as_stream(stream)));
   PP_TRY(pp_k_prepare_masks(mask, mask_frames, T, H, W, flow_mask_dilates, mask_dilates, scratch, flow_masks,
                             masks_dilated, as_stream(stream)));
   e.launches += 4;
-  e.arena.release(mark);
   return PP_OK;
 }
 
@@ -224,7 +312,7 @@ int pp_op_attention(pp_handle h, const void* qkv_f16, const void* pkv_f16, void*
   const int nh = pp_ceil_div(gh, 5) * 5, nw = pp_ceil_div(gw, 9) * 9;
   std::vector<int> ring;
   pp_build_ring_indices(nh, nw, ring);
-  const size_t mark = e.arena.mark();
+  ArenaGuard guard(e.arena);
   int* ring_dev;
   PP_TRY(pp_alloc(e, &ring_dev, ring.size(), "ring indices"));
   PP_CUDA_CHECK(cudaMemcpyAsync(ring_dev, ring.data(), ring.size() * sizeof(int), cudaMemcpyHostToDevice,
@@ -242,7 +330,6 @@ int pp_op_attention(pp_handle h, const void* qkv_f16, const void* pkv_f16, void*
                          win_flags_dev, ring_dev, meta_dev, meta_dev + 1, 1, t, gh, gw, nh, nw, n_pool, parity,
                          key_tab, key_stride, as_stream(stream));
   PP_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
-  e.arena.release(mark);
   e.launches++;
   return r;
 }

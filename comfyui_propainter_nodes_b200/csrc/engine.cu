@@ -113,6 +113,11 @@ int PPConvCall::run(cudaStream_t st) {
   p.OW = (p.W + 2 * p.pw - p.dw * (p.kw - 1) - 1) / p.sw + 1;
   eng->launches++;
   const double rows = (double)p.N * p.OH * p.OW;
-  PPProfScope ps(*eng, "conv:" + name, rows, 2.0 * rows * p.Cout_g * p.groups * p.kh * p.kw * p.Cin, 0.0, st);
+  double macs = (double)p.Cout_g * p.groups * p.kh * p.kw * p.Cin;
+  if (eng->profile) {
+    auto it = eng->convs.find(name);
+    if (it != eng->convs.end() && it->second.macs_per_pixel > 0.0) macs = it->second.macs_per_pixel;
+  }
+  PPProfScope ps(*eng, "conv:" + name, rows, 2.0 * rows * macs, 0.0, st);
   return pp_launch_conv(p, st);
 }

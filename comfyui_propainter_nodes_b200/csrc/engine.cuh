@@ -11,6 +11,9 @@ struct PPPackedConv {
   const __half* w = nullptr;   // swizzled tile image [groups][num_kc][cout_g_pad][64]
   const float* b = nullptr;    // [groups*cout_g] or null
   int cout_g = 0, cout_g_pad = 0, bn = 0, cin_g = 0, kh = 1, kw = 1, groups = 1;
+  // multiply-adds per output pixel of the REFERENCE layer (unpadded channels, real group structure); 0 = unknown,
+  // the bench then falls back to the packed shape.  Only used for the roofline's algorithmic flop count.
+  double macs_per_pixel = 0.0;
 };
 
 struct PPTensor {
@@ -53,6 +56,9 @@ struct PPEngine {
     int* win_flags = nullptr;     // [n_win]
     int gh = 0, gw = 0, nh = 0, nw = 0, ph = 0, pw = 0;
   } gen;
+  // multi-GPU (comm.cu): NCCL communicator (ncclComm_t, opaque here) of this engine's process group
+  void* comm = nullptr;
+  int rank = 0, world = 1;
   long long launches = 0;  // kernels launched by this engine (for bench accounting)
   // optional per-kernel timing (CUDA events on the launch stream), see pp_profile_* in capi.cu
   struct ProfRec {
@@ -125,6 +131,13 @@ int pp_fuse_upsample();
 
 void pp_build_ring_indices(int nh, int nw, std::vector<int>& out);
 
+// ---- multi-GPU exchange (comm.cu) -----------------------------------------------------------------
+int pp_comm_unique_id_impl(void* out128);
+int pp_comm_init_impl(PPEngine& e, const void* unique_id, int rank, int world);
+int pp_comm_destroy_impl(PPEngine& e);
+int pp_comm_all_gather_rows_impl(PPEngine& e, void* buf, const long long* rows, size_t row_bytes, int first_rank,
+                                 int n_members, cudaStream_t st);
+
 // ---- stages ---------------------------------------------------------------------------------------
 int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int iters, float* flows_f, float* flows_b,
                   cudaStream_t st);
@@ -134,7 +147,8 @@ int pp_stage_image_propagate(PPEngine& e, const float* frames, const float* mask
                              const float* flows_b, int T, int H, int W, float* upd_frames, float* upd_masks,
                              cudaStream_t st);
 int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, const float* masks_upd,
-                 const float* flows_f, const float* flows_b, int T, int H, int W, cudaStream_t st);
+                 const float* flows_f, const float* flows_b, int T, int H, int W, const unsigned char* need,
+                 cudaStream_t st);
 int pp_stage_gen_window(PPEngine& e, const int* frame_ids, int t, int l_t, __half* pred /*[l_t][H][W][8]*/,
                   cudaStream_t st);
 int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const int* win_lt, int n_windows,

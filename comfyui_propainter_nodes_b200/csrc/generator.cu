@@ -66,7 +66,8 @@ int pp_stage_gen_end(PPEngine& e) {
 }
 
 int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, const float* masks_upd,
-                 const float* flows_f, const float* flows_b, int T, int H, int W, cudaStream_t st) {
+                 const float* flows_f, const float* flows_b, int T, int H, int W, const unsigned char* need,
+                 cudaStream_t st) {
   PP_REQUIRE(H % 8 == 0 && W % 8 == 0, "generator: size %dx%d must be a multiple of 8", W, H);
   pp_stage_gen_end(e);
   PPEngine::GenSession& g = e.gen;
@@ -119,13 +120,32 @@ int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, 
   PP_TRY(pp_alloc(e, &b12, (size_t)chunk * P4 * 384, "enc b12"));
   PP_TRY(pp_alloc(e, &b14, (size_t)chunk * P4 * 256, "enc b14"));
   const long long HW = (long long)H * W;
-  for (int f0 = 0; f0 < T; f0 += chunk) {
-    const int n = (f0 + chunk <= T) ? chunk : T - f0;
+  // frames to encode: all of them, or (multi-GPU window shards) only the ones this rank's windows touch.  The needed
+  // frames are packed into chunks; a chunk is a list of runs of consecutive frames (local frames of a window form one
+  // run, the strided reference frames are runs of one).
+  std::vector<int> todo;
+  for (int f = 0; f < T; ++f)
+    if (need == nullptr || need[f]) todo.push_back(f);
+  __half* enc_tmp = nullptr;
+  if (need != nullptr) PP_TRY(pp_alloc(e, &enc_tmp, (size_t)chunk * P4 * 128, "enc packed output"));
+  for (size_t c0 = 0; c0 < todo.size(); c0 += chunk) {
+    const int n = (int)((c0 + chunk <= todo.size()) ? chunk : todo.size() - c0);
+    struct Run { int frame, slot, len; };
+    std::vector<Run> runs;
+    for (int i = 0; i < n; ++i) {
+      const int f = todo[c0 + i];
+      if (!runs.empty() && runs.back().frame + runs.back().len == f) runs.back().len++;
+      else runs.push_back(Run{f, i, 1});
+    }
     // input = cat(frame[3], mask_in[1], mask_updated[1]) (propainter.py:374-383), padded to 8 channels
-    PP_TRY(pp_k_nchw_f32_to_nhwc_f16(frames + (size_t)f0 * 3 * HW, x8, n, 3, H, W, 8, 0, 8, st));
-    PP_TRY(pp_k_nchw_f32_to_nhwc_f16(masks_in + (size_t)f0 * HW, x8, n, 1, H, W, 8, 3, 1, st));
-    PP_TRY(pp_k_nchw_f32_to_nhwc_f16(masks_upd + (size_t)f0 * HW, x8, n, 1, H, W, 8, 4, 1, st));
-    e.launches += 3;
+    for (const Run& r : runs) {
+      __half* dst = x8 + (size_t)r.slot * HW * 8;
+      PP_TRY(pp_k_nchw_f32_to_nhwc_f16(frames + (size_t)r.frame * 3 * HW, dst, r.len, 3, H, W, 8, 0, 8, st));
+      PP_TRY(pp_k_nchw_f32_to_nhwc_f16(masks_in + (size_t)r.frame * HW, dst, r.len, 1, H, W, 8, 3, 1, st));
+      PP_TRY(pp_k_nchw_f32_to_nhwc_f16(masks_upd + (size_t)r.frame * HW, dst, r.len, 1, H, W, 8, 4, 1, st));
+      e.launches += 3;
+    }
+    __half* enc_out = (runs.size() == 1) ? g.enc + (size_t)runs[0].frame * P4 * 128 : enc_tmp;
     const float s = 0.2f;
     PP_TRY(PPConvCall(e, "gen.encoder.0", n, H, W).in(x8, 8, 0, 8).geom(2, 2, 1, 1).out(a0, 64, 0).act(PP_ACT_LRELU, s).run(st));
     PP_TRY(PPConvCall(e, "gen.encoder.2", n, h2, w2).in(a0, 64, 0, 64).out(a1, 64, 0).act(PP_ACT_LRELU, s).run(st));
@@ -141,7 +161,11 @@ int pp_stage_gen_begin(PPEngine& e, const float* frames, const float* masks_in, 
     PP_TRY(PPConvCall(e, "gen.encoder.14", n, h4, w4).in(x0, 256, 0, 256).in(b12, 384, 0, 384)
                .out(b14, 256, 0).act(PP_ACT_LRELU, s).run(st));
     PP_TRY(PPConvCall(e, "gen.encoder.16", n, h4, w4).in(x0, 256, 0, 256).in(b14, 256, 0, 256)
-               .out(g.enc + (size_t)f0 * P4 * 128, 128, 0).act(PP_ACT_LRELU, s).run(st));
+               .out(enc_out, 128, 0).act(PP_ACT_LRELU, s).run(st));
+    if (runs.size() > 1)
+      for (const Run& r : runs)
+        PP_CUDA_CHECK(cudaMemcpyAsync(g.enc + (size_t)r.frame * P4 * 128, enc_tmp + (size_t)r.slot * P4 * 128,
+                                      (size_t)r.len * P4 * 128 * sizeof(__half), cudaMemcpyDeviceToDevice, st));
   }
   e.arena.release(m1);
   return PP_OK;
@@ -322,6 +346,13 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
   PP_TRY(pp_k_window_flags(g.mask_in4, 8, 0, tab_dev + o_f0, tab_dev + o_lt, n_sw, h4, w4, gh, gw, nh / WIN_H, nw / WIN_W,
                            flags, st));
   e.launches++;
+  // profiling only: how many 5x9 windows of each sliding window are masked (data dependent) -> real attention flops
+  std::vector<int> flags_host;
+  if (e.profile) {
+    flags_host.resize((size_t)n_sw * n_win);
+    PP_CUDA_CHECK(cudaMemcpyAsync(flags_host.data(), flags, flags_host.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PP_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
 
   // gather table scratch of the tcgen05 attention kernel: [5x9 windows][keys of a masked window]
   const int key_stride = ((t_max + 1) / 2) * (193 + np);
@@ -342,10 +373,16 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
     PP_TRY(pp_k_pool_tokens(xn, (const float*)pwt, (const float*)pbs, pooled, TT, nh, nw, g.ph, g.pw, 512, st));
     PP_TRY(PPConvCall(e, b + "kv", 1, 1, TT * np).in(pooled, 512, 0, 512).out(pkv, 1024, 0).run(st));
     {
-      // flops if every 5x9 window were masked (upper bound; the masked fraction is data dependent)
+      // 4 q k 128 per head and 5x9 window (4 heads): masked windows attend from all t*45 queries to the keys of every
+      // 2nd frame (45 own + 148 ring + pooled tokens each), unmasked windows only to the 45 keys of their own frame
       double fl = 0;
-      for (int w = 0; w < n_sw; ++w)
-        fl += 4.0 * win_t[w] * nh * nw * ((win_t[w] - blk % 2 + 1) / 2) * (193 + np) * 512;
+      for (int w = 0; e.profile && w < n_sw; ++w) {
+        int masked = 0;
+        for (int k = 0; k < n_win; ++k) masked += flags_host[(size_t)w * n_win + k] != 0;
+        const double q = 45.0 * win_t[w];
+        fl += masked * 4.0 * q * ((win_t[w] - blk % 2 + 1) / 2) * (193 + np) * 512;
+        fl += (n_win - masked) * 4.0 * q * 45.0 * 512;
+      }
       PPProfScope ps(e, "attention", (double)rows_pad, fl, 0.0, st);
       PP_TRY(pp_k_attention(qkv, qkv + 512, qkv + 1024, 1536, pkv, pkv + 512, 1024, att, 512, flags, g.ring_idx,
                             tab_dev + o_foff, tab_dev + o_t, n_sw, t_max, gh, gw, nh, nw, np, blk % 2, key_tab, key_stride,

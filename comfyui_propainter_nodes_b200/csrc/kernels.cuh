@@ -67,7 +67,7 @@ int pp_k_attention(const __half* q, const __half* k, const __half* v, int qkv_cs
                    const int* sw_frame_off, const int* sw_t, int n_sliding, int t_max, int gh, int gw, int nh, int nw,
                    int n_pool, int t_parity, int* key_tab, int key_tab_stride, cudaStream_t st);
 int pp_k_composite(const __half* pred, int pred_cs, const float* masks, const uint8_t* orig, uint8_t* comp,
-                   const int* frame_ids, const int* first_visit, int lt, int H, int W, cudaStream_t st);
+                   const int* frame_ids, const int* first_visit, int lt, int H, int W, int half_math, cudaStream_t st);
 
 // ---- device pre/post-processing (kernels_pre.cu) --------------------------------------------------
 int pp_k_quantize_frames(const float* img, uint8_t* u8, float* frames, int T, int H, int W, cudaStream_t st);

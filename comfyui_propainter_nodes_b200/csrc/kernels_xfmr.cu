@@ -203,7 +203,7 @@ __global__ void fold7x7s3(const __half* __restrict__ x, int cs, __half* __restri
 __global__ void composite(const __half* __restrict__ pred, int pred_cs, const float* __restrict__ masks,
                           const uint8_t* __restrict__ orig, uint8_t* __restrict__ comp,
                           const int* __restrict__ frame_ids, const int* __restrict__ first_visit, int lt,
-                          long long HW) {
+                          long long HW, int half_math) {
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= (long long)lt * HW) return;
   const int i = idx / HW;
@@ -216,7 +216,15 @@ __global__ void composite(const __half* __restrict__ pred, int pred_cs, const fl
   const int first = first_visit[i];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float v = (__half2float(pr[c]) + 1.f) / 2.f * 255.f;
+    // fp16="disable": the reference holds float32 here.  fp16="enable": (pred + 1) / 2 is evaluated in half on the
+    // device and the numpy "* 255" stays half too -- two extra roundings that move ~6 % of the bytes by one
+    float v;
+    if (half_math) {
+      const __half a = __float2half_rn(__half2float(pr[c]) + 1.f);   // half add, round to nearest even
+      v = __half2float(__float2half_rn(__half2float(a) * 0.5f * 255.f));   // /2 is exact in half
+    } else {
+      v = (__half2float(pr[c]) + 1.f) / 2.f * 255.f;
+    }
     const uint8_t pu = (uint8_t)(int)v;  // astype(np.uint8): truncation (values are within [0,255])
     const uint8_t sel = (uint8_t)(pu * m + og[c] * (1 - m));
     cp[c] = first ? sel : (uint8_t)(int)((float)cp[c] * 0.5f + (float)sel * 0.5f);
@@ -264,9 +272,10 @@ int pp_k_fold(const __half* x, int cs, __half* out, int t, int H, int W, int C, 
 }
 
 int pp_k_composite(const __half* pred, int pred_cs, const float* masks, const uint8_t* orig, uint8_t* comp,
-                   const int* frame_ids, const int* first_visit, int lt, int H, int W, cudaStream_t st) {
+                   const int* frame_ids, const int* first_visit, int lt, int H, int W, int half_math, cudaStream_t st) {
   const long long HW = (long long)H * W;
-  composite<<<nblocks(HW * lt), TPB, 0, st>>>(pred, pred_cs, masks, orig, comp, frame_ids, first_visit, lt, HW);
+  composite<<<nblocks(HW * lt), TPB, 0, st>>>(pred, pred_cs, masks, orig, comp, frame_ids, first_visit, lt, HW,
+                                              half_math);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

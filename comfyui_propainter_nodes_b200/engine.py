@@ -30,16 +30,23 @@ _SIGNATURES = {
     "pp_version": (_CP, []),
     "pp_create": (_I, [_I, _VP, _SZ, ctypes.POINTER(_VP)]),
     "pp_destroy": (_I, [_VP]),
+    "pp_set_workspace": (_I, [_VP, _VP, _SZ]),
+    "pp_comm_unique_id": (_I, [_VP]),
+    "pp_comm_init": (_I, [_VP, _VP, _I, _I]),
+    "pp_comm_destroy": (_I, [_VP]),
+    "pp_comm_all_gather_rows": (_I, [_VP, _VP, ctypes.POINTER(_LL), _SZ, _I, _I, _VP]),
     "pp_register_conv": (_I, [_VP, _CP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I]),
     "pp_register_tensor": (_I, [_VP, _CP, _VP, _SZ]),
+    "pp_set_conv_macs": (_I, [_VP, _CP, ctypes.c_double]),
     "pp_raft_bidir": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     "pp_flow_complete": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pp_image_propagate": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pp_gen_begin": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "pp_gen_begin_subset": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, ctypes.c_char_p, _VP]),
     "pp_gen_window": (_I, [_VP, ctypes.POINTER(_I), _I, _I, _VP, _VP]),
     "pp_gen_run": (_I, [_VP, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _VP, _VP]),
     "pp_gen_end": (_I, [_VP]),
-    "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "pp_preprocess": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "pp_postprocess": (_I, [_VP, _VP, _VP, _LL, _VP]),
     "pp_launch_count": (_LL, [_VP]),
@@ -142,8 +149,10 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
     convs: Dict[str, tuple] = {}
     tens: Dict[str, torch.Tensor] = {}
 
-    def add(name, w, b, groups=1, cin_map=None):
-        convs[name] = (w.float(), None if b is None else b.float(), groups, cin_map)
+    def add(name, w, b, groups=1, cin_map=None, macs=None):
+        # macs: multiply-adds per output pixel of the reference layer (default: the weight tensor as given)
+        convs[name] = (w.float(), None if b is None else b.float(), groups, cin_map,
+                       float(w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3]) if macs is None else float(macs))
 
     # ------------------------------------------------------------------ RAFT
     r = {(k[7:] if k.startswith("module.") else k): v.float() for k, v in raft_sd.items()}
@@ -227,7 +236,7 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
                 rows = slice(k * (cout // gr), (k + 1) * (cout // gr))
                 dense[rows, k * nx:(k + 1) * nx] = w[rows, :nx]
                 dense[rows, 256 + k * npv:256 + (k + 1) * npv] = w[rows, nx:]
-            add("gen.encoder.14", dense, g["encoder.layers.14.bias"], 1, None)
+            add("gen.encoder.14", dense, g["encoder.layers.14.bias"], 1, None, macs=w.numel())
             continue
         add(f"gen.encoder.{i}", w, g[f"encoder.layers.{i}.bias"], gr, _pad_map(5, 8) if i == 0 else None)
     for dst, src in (("0", "0.conv"), ("2", "2"), ("4", "4.conv"), ("6", "6")):
@@ -279,7 +288,11 @@ def _ptr(t):
 class Engine:
     """One engine per process/GPU.  Owns the workspace arena and the packed weights."""
 
-    def __init__(self, device: torch.device | str | int = "cuda:0", workspace_gb: float = 48.0):
+    MIN_WORKSPACE = 256 << 20
+
+    def __init__(self, device: torch.device | str | int = "cuda:0", workspace_gb: float | None = None):
+        """``workspace_gb``: fixed size of the scratch arena; None = start at 256 MiB and let ``reserve_for_clip``
+        size it from (T, H, W) before each clip (what the node path does)."""
         self.lib = load_library()
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -287,13 +300,50 @@ class Engine:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._keep = []
-        total = torch.cuda.get_device_properties(self.device).total_memory
-        nbytes = int(min(workspace_gb * (1 << 30), total * 0.6))
+        self._total_mem = torch.cuda.get_device_properties(self.device).total_memory
+        self.fixed_workspace = workspace_gb is not None
+        nbytes = self.MIN_WORKSPACE if workspace_gb is None else int(min(workspace_gb * (1 << 30), self._total_mem * 0.8))
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         h = ctypes.c_void_p()
         self._check(self.lib.pp_create(self.device.index, _ptr(self.workspace), nbytes, ctypes.byref(h)))
         self.h = h
         self.conv_meta: Dict[str, dict] = {}
+
+    # -- workspace sizing
+    @staticmethod
+    def clip_workspace_bytes(T: int, H: int, W: int) -> int:
+        """Arena size that lets every stage of a T x H x W clip run in its widest batching (measured peaks: 24.3 GB at
+        80 x 640x360, 92 GB at 80 x 1280x720 => ~1.3 kB per frame-pixel; clips beyond ~100 frames are processed in
+        sub-batches of windows / chunks of sub-videos, so the estimate saturates there)."""
+        return int(1400 * min(T, 100) * H * W + (2 << 30))
+
+    def set_workspace_bytes(self, nbytes: int) -> None:
+        """Re-allocate the arena (no generator session may be open)."""
+        nbytes = max(int(nbytes), self.MIN_WORKSPACE)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.workspace = None                       # release before allocating: never hold old + new together
+        torch.cuda.empty_cache()
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.pp_set_workspace(self.h, _ptr(ws), nbytes))
+        self.workspace = ws
+
+    def reserve_for_clip(self, T: int, H: int, W: int) -> int:
+        """Grow the arena for a clip when it was created without a fixed size.  Capped at 80 % of the device memory;
+        when the cap (or a fixed size) is below the estimate the stages fall back to smaller batches
+        (RAFT pair batches, encoder / decoder frame chunks, sub-batches of sliding windows)."""
+        if self.fixed_workspace:
+            return self.workspace.numel()
+        free, _ = torch.cuda.mem_get_info(self.device)
+        have = self.workspace.numel()
+        want = min(self.clip_workspace_bytes(T, H, W), int(self._total_mem * 0.8), int((free + have) * 0.9))
+        if want > have:
+            self.set_workspace_bytes(want)
+        return self.workspace.numel()
+
+    def release_workspace(self) -> None:
+        """Shrink the arena back to its minimum (gives the HBM back between node executions when asked to)."""
+        if not self.fixed_workspace and self.workspace.numel() > self.MIN_WORKSPACE:
+            self.set_workspace_bytes(self.MIN_WORKSPACE)
 
     # -- helpers
     def _check(self, rc: int):
@@ -307,6 +357,8 @@ class Engine:
         if getattr(self, "h", None):
             self.lib.pp_destroy(self.h)
             self.h = None
+        self.workspace = None
+        self._keep = []
 
     def __del__(self):
         try:
@@ -315,7 +367,7 @@ class Engine:
             pass
 
     # -- weights
-    def register_conv(self, name, w, b, groups=1, cin_map=None):
+    def register_conv(self, name, w, b, groups=1, cin_map=None, macs=None):
         packed, meta = pack_conv_weight(w, groups, cin_map)
         packed = packed.to(self.device)
         bias = None if b is None else b.detach().float().contiguous().to(self.device)
@@ -324,6 +376,7 @@ class Engine:
         self._check(self.lib.pp_register_conv(self.h, name.encode(), _ptr(packed), _ptr(bias), meta["cout_g"],
                                               meta["cout_g_pad"], meta["bn"], meta["cin_g"], meta["kh"], meta["kw"],
                                               meta["groups"]))
+        self._check(self.lib.pp_set_conv_macs(self.h, name.encode(), float(w.numel() if macs is None else macs)))
 
     def register_tensor(self, name, t):
         t = t.detach().float().contiguous().to(self.device)
@@ -341,11 +394,11 @@ class Engine:
 
     def load_weights(self, raft_sd, rfc_sd, gen_sd):
         convs, tens = build_layers(raft_sd, rfc_sd, gen_sd)
-        for name, (w, b, groups, cin_map) in convs.items():
+        for name, (w, b, groups, cin_map, macs) in convs.items():
             if name in self.PAD64_CONVS:
                 cin_map = list(cin_map) if cin_map is not None else list(range(w.shape[1]))
                 cin_map += [-1] * ((-len(cin_map)) % 64)
-            self.register_conv(name, w, b, groups, cin_map)
+            self.register_conv(name, w, b, groups, cin_map, macs)
         for name, t in tens.items():
             self.register_tensor(name, t)
         return self
@@ -354,12 +407,17 @@ class Engine:
     def _f32(self, t):
         return t.to(device=self.device, dtype=torch.float32).contiguous()
 
-    def raft_bidir(self, frames: torch.Tensor, iters: int):
-        """frames [T,3,H,W] in [-1,1] -> (flows_f, flows_b) [T-1,2,H,W]."""
+    def raft_bidir(self, frames: torch.Tensor, iters: int, out=None):
+        """frames [T,3,H,W] in [-1,1] -> (flows_f, flows_b) [T-1,2,H,W] (written into `out` when given: contiguous
+        float32 views, e.g. a rank's shard of the full flow buffers)."""
         frames = self._f32(frames)
         T, _, H, W = frames.shape
-        ff = torch.empty(T - 1, 2, H, W, device=self.device, dtype=torch.float32)
-        fb = torch.empty_like(ff)
+        if out is not None:
+            ff, fb = out
+            assert ff.is_contiguous() and fb.is_contiguous() and ff.dtype == torch.float32 and ff.shape == (T - 1, 2, H, W)
+        else:
+            ff = torch.empty(T - 1, 2, H, W, device=self.device, dtype=torch.float32)
+            fb = torch.empty_like(ff)
         self._check(self.lib.pp_raft_bidir(self.h, _ptr(frames), T, H, W, int(iters), _ptr(ff), _ptr(fb), self._stream()))
         return ff, fb
 
@@ -380,12 +438,19 @@ class Engine:
                                                 _ptr(uf), _ptr(um), self._stream()))
         return uf, um
 
-    def gen_begin(self, updated_frames, masks_dilated, updated_masks, flows_f, flows_b):
+    def gen_begin(self, updated_frames, masks_dilated, updated_masks, flows_f, flows_b, frames_needed=None):
+        """Open a generator session over the clip.  ``frames_needed``: frame ids to encode (default all); the windows
+        given to gen_run must only touch those."""
         a = [self._f32(x) for x in (updated_frames, masks_dilated, updated_masks, flows_f, flows_b)]
         T, _, H, W = a[0].shape
         self._gen_shape = (T, H, W)
         self._gen_inputs = a  # keep alive for the session
-        self._check(self.lib.pp_gen_begin(self.h, *[_ptr(x) for x in a], T, H, W, self._stream()))
+        self._gen_needed = None if frames_needed is None else set(int(i) for i in frames_needed)
+        if frames_needed is None:
+            self._check(self.lib.pp_gen_begin(self.h, *[_ptr(x) for x in a], T, H, W, self._stream()))
+        else:
+            need = bytes(1 if i in self._gen_needed else 0 for i in range(T))
+            self._check(self.lib.pp_gen_begin_subset(self.h, *[_ptr(x) for x in a], T, H, W, need, self._stream()))
 
     def gen_window(self, frame_ids, l_t: int) -> torch.Tensor:
         """-> fp16 [l_t,H,W,4] (rgb in [-1,1], lane 3 unused)."""
@@ -395,11 +460,63 @@ class Engine:
         self._check(self.lib.pp_gen_window(self.h, ids, len(frame_ids), int(l_t), _ptr(pred), self._stream()))
         return pred
 
+    def gen_slot_bytes(self) -> int:
+        """Workspace one (window, frame) slot of pp_gen_run needs: window-major features, token / qkv / FFN rows of
+        the transformer, and its share of the feature-propagation and decoder buffers (generator.cu)."""
+        T, H, W = self._gen_shape
+        p4 = (H // 4) * (W // 4)
+        gh, gw = (H // 4 + 6 - 7) // 3 + 1, (W // 4 + 6 - 7) // 3 + 1
+        rows_pad = -(-gh // 5) * 5 * (-(-gw // 9) * 9)
+        xfmr = p4 * (256 + 80) + gh * gw * 2 * (512 * 3 + 1960) + rows_pad * 2 * (512 + 1536)
+        featprop = p4 * 2 * (128 * 5 + 264 + 432 + 1152 + 128 * 3)
+        return int(1.25 * (xfmr + featprop))
+
+    def gen_batches(self, windows, budget_bytes: int):
+        """Split the schedule into consecutive sub-batches whose slots fit `budget_bytes` (windows are independent;
+        the composite order is the window order, which consecutive sub-batches keep)."""
+        per_slot = self.gen_slot_bytes()
+        out, cur, used = [], [], 0
+        for w in windows:
+            need = (len(w[0]) + len(w[1])) * per_slot
+            if cur and used + need > budget_bytes:
+                out.append(cur)
+                cur, used = [], 0
+            cur.append(w)
+            used += need
+        if cur:
+            out.append(cur)
+        return out
+
     def gen_run(self, windows) -> torch.Tensor:
-        """All sliding windows in one batched pass.  windows = [(neighbor_ids, ref_ids), ...]
-        -> fp16 [sum(len(neighbor_ids)), H, W, 4] in window order."""
+        """Sliding windows in batched passes.  windows = [(neighbor_ids, ref_ids), ...]
+        -> fp16 [sum(len(neighbor_ids)), H, W, 4] in window order.
+
+        One engine pass covers as many windows as the workspace holds (all 16 of an 80-frame 640x360 clip); a long
+        or large clip is split into consecutive sub-batches, down to one window per pass, before giving up --
+        the reference runs one window at a time, so anything it can process this can too."""
+        T, H, W = self._gen_shape
+        enc_bytes = T * (H // 4) * (W // 4) * (256 + 32) + (64 << 20)          # the session's resident part
+        decoder_reserve = 24 * H * W * 2 * 200                                   # room for a useful decoder chunk
+        budget = max(self.workspace.numel() - enc_bytes - decoder_reserve, self.gen_slot_bytes())
+        out = [self._gen_run_or_split(b) for b in self.gen_batches(list(windows), budget)]
+        return out[0] if len(out) == 1 else torch.cat(out, 0)
+
+    def _gen_run_or_split(self, windows) -> torch.Tensor:
+        try:
+            return self._gen_run_once(windows)
+        except RuntimeError as ex:
+            if "workspace" not in str(ex) or len(windows) == 1:
+                raise
+        half = len(windows) // 2                     # the estimate was too optimistic: halve and retry
+        return torch.cat([self._gen_run_or_split(windows[:half]), self._gen_run_or_split(windows[half:])], 0)
+
+    def _gen_run_once(self, windows) -> torch.Tensor:
         T, H, W = self._gen_shape
         flat, wt, wl = [], [], []
+        if getattr(self, "_gen_needed", None) is not None:
+            missing = {int(i) for nb, refs in windows for i in list(nb) + list(refs)} - self._gen_needed
+            if missing:
+                raise ValueError(f"gen_run: frames {sorted(missing)} were not encoded by gen_begin(frames_needed=...)")
         for nb, refs in windows:
             flat += [int(i) for i in nb] + [int(i) for i in refs]
             wt.append(len(nb) + len(refs))
@@ -413,10 +530,13 @@ class Engine:
         self._check(self.lib.pp_gen_end(self.h))
         self._gen_inputs = None
 
-    def composite(self, pred, masks_dilated, orig_u8, comp_u8, frame_ids_dev, first_visit_dev):
+    def composite(self, pred, masks_dilated, orig_u8, comp_u8, frame_ids_dev, first_visit_dev, half_math=False):
+        """half_math: reproduce the half-precision roundings of the reference's fp16="enable" mode before the uint8
+        truncation (reference propainter_inference.py:285-286 on a half tensor)."""
         l_t, H, W, _ = pred.shape
         self._check(self.lib.pp_composite(self.h, _ptr(pred), _ptr(masks_dilated), _ptr(orig_u8), _ptr(comp_u8),
-                                          _ptr(frame_ids_dev), _ptr(first_visit_dev), l_t, H, W, self._stream()))
+                                          _ptr(frame_ids_dev), _ptr(first_visit_dev), l_t, H, W, int(bool(half_math)),
+                                          self._stream()))
 
     def preprocess(self, image, mask, flow_mask_dilates: int, mask_dilates: int):
         """Device version of convert_image_to_frames + prepare_frames_and_masks for the no-resize case.
@@ -439,6 +559,35 @@ class Engine:
         out = torch.empty(comp_u8.shape, device=self.device, dtype=torch.float32)
         self._check(self.lib.pp_postprocess(self.h, _ptr(comp_u8), _ptr(out), comp_u8.numel(), self._stream()))
         return out
+
+    # -- multi-GPU exchange (NCCL communicator inside the C library)
+    rank, world = 0, 1
+
+    def comm_unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        self._check(self.lib.pp_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == 128
+        self._check(self.lib.pp_comm_init(self.h, ctypes.create_string_buffer(unique_id, 128), int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def comm_destroy(self):
+        self._check(self.lib.pp_comm_destroy(self.h))
+        self.rank, self.world = 0, 1
+
+    def comm_all_gather_rows(self, buf: torch.Tensor, rows, first_rank: int = 0):
+        """In-place all-gather along dim 0 of the contiguous tensor `buf` among ranks
+        [first_rank, first_rank + len(rows)): member m owns rows [sum(rows[:m]), +rows[m])."""
+        assert buf.is_contiguous() and buf.shape[0] == sum(rows)
+        row_bytes = buf[0].numel() * buf.element_size() if buf.shape[0] else 0
+        if len(rows) <= 1 or row_bytes == 0:
+            return buf
+        arr = (ctypes.c_longlong * len(rows))(*[int(r) for r in rows])
+        self._check(self.lib.pp_comm_all_gather_rows(self.h, _ptr(buf), arr, row_bytes, int(first_rank), len(rows),
+                                                     self._stream()))
+        return buf
 
     @property
     def launch_count(self) -> int:

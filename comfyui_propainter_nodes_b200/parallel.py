@@ -22,6 +22,19 @@ import torch
 import torch.distributed as dist
 
 
+def init_engine_comm(engine, group=None) -> None:
+    """Create the engine's own NCCL communicator (pp_comm_init): rank 0 makes the ncclUniqueId inside the C library,
+    torch.distributed only carries the 128 bytes to the other ranks."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.comm_init(box[0], rank, world)
+
+
+def destroy_engine_comm(engine) -> None:
+    engine.comm_destroy()
+
+
 def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous near-equal split of range(n): returns [lo, hi) of `rank` (earlier ranks get the remainder)."""
     base, rem = divmod(n, world)
@@ -67,56 +80,89 @@ def composite_order(schedule) -> Tuple[List[int], List[int]]:
     return ids, first
 
 
+def gather_rows(eng, buf: torch.Tensor, rows: Sequence[int], first_rank: int = 0, group=None) -> torch.Tensor:
+    """In-place all-gather of row blocks of `buf` (member m of the rank range owns rows[m] rows): through the engine's
+    NCCL communicator (pp_comm_all_gather_rows) when it has one, else through torch.distributed (CPU/gloo tests)."""
+    if len(rows) <= 1:
+        return buf
+    if getattr(eng, "world", 1) > 1:
+        return eng.comm_all_gather_rows(buf, rows, first_rank)
+    rank = dist.get_rank(group) - first_rank
+    lo = sum(rows[:rank])
+    buf.copy_(all_gather_variable(buf[lo:lo + rows[rank]].clone(), rows, group))
+    return buf
+
+
 def inpaint_clip_distributed(models, frames, flow_masks, masks_dilated, orig_u8, cfg, group=None) -> torch.Tensor:
     """Strong-scaling pass over ONE clip shared by all ranks of `group`.  Inputs are replicated on every rank
     (reference layouts, see propainter_inference.process_inpainting); returns the composited uint8 frames
     [T,H,W,3] on every rank."""
     from . import propainter_inference as PI
 
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     eng = models.raft_model.engine
+    if getattr(eng, "world", 1) > 1:
+        world, rank = eng.world, eng.rank
+    else:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
     T = cfg.video_length
+    H, W = frames.shape[-2:]
+    dev = eng.device
 
-    # ---- RAFT: pairs [lo, hi) need frames [lo, hi]
+    # ---- RAFT: pairs [lo, hi) need frames [lo, hi]; every rank writes its shard into the full buffers, one
+    #      all-gather per direction completes them (fp32: the N-GPU flows equal the 1-GPU flows bit for bit)
     n_pairs = T - 1
     lo, hi = shard_range(n_pairs, world, rank)
+    ff = torch.empty(n_pairs, 2, H, W, device=dev, dtype=torch.float32)
+    fb = torch.empty_like(ff)
     if hi > lo:
-        ff, fb = eng.raft_bidir(frames[0, lo:hi + 1], cfg.raft_iter)
-    else:
-        H, W = frames.shape[-2:]
-        ff = torch.zeros(0, 2, H, W, device=eng.device)
-        fb = torch.zeros_like(ff)
+        eng.raft_bidir(frames[0, lo:hi + 1], cfg.raft_iter, out=(ff[lo:hi], fb[lo:hi]))
     sizes = shard_sizes(n_pairs, world)
-    both = all_gather_variable(torch.stack([ff, fb], 1), sizes, group)   # one collective (fp32: N-GPU == 1-GPU bit for bit)
-    gt = (both[:, 0].unsqueeze(0), both[:, 1].unsqueeze(0))
+    gather_rows(eng, ff, sizes, 0, group)
+    gather_rows(eng, fb, sizes, 0, group)
+    dt = torch.float16 if cfg.use_half else torch.float32
+    gt = (ff.unsqueeze(0).to(dt), fb.unsqueeze(0).to(dt))
 
-    # ---- recurrent stages: a single chunk is computed by every rank (no exchange needed)
-    pred = PI.complete_flow(models.flow_model, gt, flow_masks, cfg.subvideo_length)
+    # ---- recurrent stages (serial in time): see complete_flow_distributed
+    pred = complete_flow_distributed(models.flow_model, gt, flow_masks, cfg.subvideo_length, rank, world, group)
     uf, um = PI.image_propagation(models.inpaint_model, frames, masks_dilated, pred, cfg)
 
-    # ---- generator windows: contiguous ranges, one all-gather of the predictions
+    # ---- generator windows: contiguous ranges; each rank encodes only the frames its windows touch and writes its
+    #      predictions into the full buffer, one all-gather completes it
     sched = PI.window_schedule(cfg)
     wlo, whi = shard_range(len(sched), world, rank)
-    md = masks_dilated[0].to(device=eng.device, dtype=torch.float32).contiguous()
-    eng.gen_begin(uf[0], md, um[0], pred[0][0], pred[1][0])
-    H, W = frames.shape[-2:]
-    if whi > wlo:
-        mine = eng.gen_run(sched[wlo:whi])
-    else:
-        mine = torch.zeros(0, H, W, 4, device=eng.device, dtype=torch.float16)
-    eng.gen_end()
+    md = masks_dilated[0].to(device=dev, dtype=torch.float32).contiguous()
     wsizes = [sum(len(nb) for nb, _ in sched[a:b]) for a, b in window_shards(len(sched), world)]
-    preds = all_gather_variable(mine, wsizes, group)
+    preds = torch.empty(sum(wsizes), H, W, 4, device=dev, dtype=torch.float16)
+    if whi > wlo:
+        need = sorted({i for nb, refs in sched[wlo:whi] for i in list(nb) + list(refs)})
+        eng.gen_begin(uf[0], md, um[0], pred[0][0], pred[1][0], frames_needed=need)
+        try:
+            o = sum(wsizes[:rank])
+            preds[o:o + wsizes[rank]] = eng.gen_run(sched[wlo:whi])
+        finally:
+            eng.gen_end()
+    gather_rows(eng, preds, wsizes, 0, group)
 
     ids, first = composite_order(sched)
-    ids_dev = torch.tensor(ids, dtype=torch.int32, device=eng.device)
-    first_dev = torch.tensor(first, dtype=torch.int32, device=eng.device)
-    orig = orig_u8.to(eng.device).contiguous()
+    ids_dev = torch.tensor(ids, dtype=torch.int32, device=dev)
+    first_dev = torch.tensor(first, dtype=torch.int32, device=dev)
+    orig = orig_u8.to(dev).contiguous()
     comp = torch.zeros_like(orig)
     o = 0
     for nb, _ in sched:
         n = len(nb)
-        eng.composite(preds[o:o + n], md, orig, comp, ids_dev[o:o + n], first_dev[o:o + n])
+        eng.composite(preds[o:o + n], md, orig, comp, ids_dev[o:o + n], first_dev[o:o + n], cfg.use_half)
         o += n
     return comp
+
+
+def complete_flow_distributed(flow_model, flows_bi, flow_masks, subvideo_length, rank, world, group=None):
+    """Flow completion of one clip on `world` ranks.  The recurrence is serial in time, so what shards is
+    (a) the independent (sub-video chunk, direction) passes and (b) inside a pass the per-frame encoder / decoder.
+    This first version computes every pass on every rank (no exchange); Engine.flow_complete_dist replaces it."""
+    from . import propainter_inference as PI
+    eng = flow_model.engine
+    if hasattr(eng, "flow_complete_dist") and getattr(eng, "world", 1) > 1:
+        return PI.complete_flow(flow_model, flows_bi, flow_masks, subvideo_length, distributed=True)
+    return PI.complete_flow(flow_model, flows_bi, flow_masks, subvideo_length)

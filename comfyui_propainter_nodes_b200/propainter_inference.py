@@ -140,8 +140,12 @@ def feature_propagation_device(inpaint_model, updated_frames, updated_masks, mas
     orig = original_frames_u8.to(dev).contiguous()
     comp = torch.zeros_like(orig)
     eng.gen_begin(updated_frames[0], md, updated_masks[0], prediction_flows[0][0], prediction_flows[1][0])
-    # every window of the schedule in one batched engine pass, then the order-dependent uint8 composite
-    preds = eng.gen_run(sched)
+    try:
+        # every window of the schedule in one batched engine pass (sub-batches when the workspace is small)
+        preds = eng.gen_run(sched)
+    finally:
+        eng.gen_end()           # the session's arena share is returned on every exit
+    # the order-dependent uint8 composite
     flat_ids, first = [], []
     visited = [False] * T
     for nb, _ in sched:
@@ -154,9 +158,8 @@ def feature_propagation_device(inpaint_model, updated_frames, updated_masks, mas
     o = 0
     for nb, _ in sched:   # windows in order: frames shared by consecutive windows are blended 0.5/0.5 in this order
         n = len(nb)
-        eng.composite(preds[o:o + n], md, orig, comp, ids_dev[o:o + n], first_dev[o:o + n])
+        eng.composite(preds[o:o + n], md, orig, comp, ids_dev[o:o + n], first_dev[o:o + n], config.use_half)
         o += n
-    eng.gen_end()
     return comp
 
 

@@ -61,6 +61,8 @@ _TUNING_WIDGETS = (
 def _run(models, frames_t, flow_masks_t, masks_dilated_t, originals_u8, cfg: ProPainterConfig):
     """originals_u8: uint8 [T,H,W,3] tensor (host or device)."""
     print(f"\nProcessing  {cfg.video_length} frames...")
+    w, h = cfg.process_size
+    models.raft_model.engine.reserve_for_clip(cfg.video_length, h, w)    # arena sized from the clip (no-op when fixed)
     updated_frames, updated_masks, flows = process_inpainting(models, frames_t, flow_masks_t, masks_dilated_t, cfg)
     comp = feature_propagation_device(models.inpaint_model, updated_frames, updated_masks, masks_dilated_t, flows,
                                       originals_u8, cfg)
@@ -74,7 +76,10 @@ def _to_host(dev: torch.Tensor) -> torch.Tensor:
     A fresh pageable 221 MB tensor (80 frames 640x360 float32) costs 60-90 ms of page faults per call on the GPU
     host (measured, tools/e2e_breakdown.py); a pinned block is recycled by the allocator once the previous result
     has been released, never while a caller still holds it, and the copy runs at PCIe rate."""
-    host = torch.empty(dev.shape, dtype=dev.dtype, device="cpu", pin_memory=True)
+    try:
+        host = torch.empty(dev.shape, dtype=dev.dtype, device="cpu", pin_memory=True)
+    except RuntimeError:        # locked-memory limit reached (results held by a caller stay pinned): pageable copy
+        return dev.cpu()
     host.copy_(dev, non_blocking=True)
     torch.cuda.current_stream(dev.device).synchronize()
     return host
@@ -105,8 +110,9 @@ class ProPainterInpaint:
         cfg = ProPainterConfig(ref_stride, neighbor_length, subvideo_length, raft_iter, fp16, n, device,
                                icfg.process_size)
         models = initialize_models(cfg.device, cfg.fp16)
-        if tuple(icfg.process_size) == tuple(input_size):
-            # no resize: quantisation and mask dilation run on the device with the same integer semantics
+        if tuple(icfg.process_size) == tuple(input_size) and mask.dtype == torch.float32:
+            # no resize: quantisation and mask dilation run on the device with the same integer semantics (float32
+            # masks only: the reference scales only those by 255, other dtypes go to PIL unscaled -- host path below)
             ft, fm, md, orig = models.raft_model.engine.preprocess(image, mask, flow_mask_dilates, mask_dilates)
         else:
             # PIL bicubic resize on the host keeps the reference's resampling bit-identical

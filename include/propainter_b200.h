@@ -43,6 +43,9 @@ PP_API const char* pp_version(void);
  * [workspace, workspace + workspace_bytes) (256-byte aligned). */
 PP_API int pp_create(int device, void* workspace, size_t workspace_bytes, pp_handle* out);
 PP_API int pp_destroy(pp_handle h);
+/* Replace the scratch arena (grow it for a larger clip, or shrink it after one); the previous buffer may be freed by
+ * the caller once this returns.  Fails while a generator session is open. */
+PP_API int pp_set_workspace(pp_handle h, void* workspace, size_t workspace_bytes);
 
 /* Register packed weights (device memory owned by the caller, must outlive the handle).
  * `w` is the 128B-swizzled tile image produced by comfyui_propainter_nodes_b200.weights_pack,
@@ -50,6 +53,21 @@ PP_API int pp_destroy(pp_handle h);
 PP_API int pp_register_conv(pp_handle h, const char* name, const void* w, const float* bias, int cout_g, int cout_g_pad,
                      int bn, int cin_g, int kh, int kw, int groups);
 PP_API int pp_register_tensor(pp_handle h, const char* name, const void* ptr, size_t bytes);
+/* Multiply-adds per output pixel of the reference layer behind a registered conv (unpadded channels, real groups);
+ * only feeds the algorithmic flop count of pp_profile_dump. */
+PP_API int pp_set_conv_macs(pp_handle h, const char* name, double macs_per_pixel);
+
+/* ---- multi-GPU: one process per GPU, an NCCL communicator per engine ------------------------
+ * Rank 0 calls pp_comm_unique_id and ships the 128 bytes to the other ranks (any host transport); every rank then
+ * calls pp_comm_init(h, id, rank, world).  NCCL is resolved with dlopen at run time (the process' own copy first). */
+PP_API int pp_comm_unique_id(void* out128);
+PP_API int pp_comm_init(pp_handle h, const void* unique_id128, int rank, int world);
+PP_API int pp_comm_destroy(pp_handle h);
+/* In-place all-gather of uneven row blocks among ranks [first_rank, first_rank + n_members): `buf` holds
+ * sum(rows_per_member) rows of row_bytes, member m has written its own block; on return (stream order) every member
+ * holds all blocks.  One NCCL send/recv group over NVLink; ranks outside the range return at once. */
+PP_API int pp_comm_all_gather_rows(pp_handle h, void* buf, const long long* rows_per_member, size_t row_bytes,
+                                   int first_rank, int n_members, void* stream);
 
 /* frames [T,3,H,W] in [-1,1]  ->  flows_f, flows_b [T-1,2,H,W]. */
 PP_API int pp_raft_bidir(pp_handle h, const float* frames, int T, int H, int W, int iters, float* flows_f, float* flows_b,
@@ -64,6 +82,11 @@ PP_API int pp_image_propagate(pp_handle h, const float* frames, const float* mas
 /* Generator session over one clip: encodes all T frames once. */
 PP_API int pp_gen_begin(pp_handle h, const float* updated_frames, const float* masks_dilated, const float* updated_masks,
                  const float* flows_f, const float* flows_b, int T, int H, int W, void* stream);
+/* Same, encoding only the frames with frames_needed[f] != 0 (host array of T bytes): a rank that runs a shard of the
+ * sliding windows encodes the frames those windows touch; windows passed to pp_gen_run must stay inside that set. */
+PP_API int pp_gen_begin_subset(pp_handle h, const float* updated_frames, const float* masks_dilated,
+                               const float* updated_masks, const float* flows_f, const float* flows_b, int T, int H, int W,
+                               const unsigned char* frames_needed, void* stream);
 /* One sliding window: frame_ids[0..l_t) are consecutive local frames, frame_ids[l_t..t) reference frames
  * (host array).  pred is fp16 [l_t][H][W][4] (rgb in [-1,1] + 1 unused lane). */
 PP_API int pp_gen_window(pp_handle h, const int* frame_ids, int t, int l_t, void* pred_f16, void* stream);
@@ -74,9 +97,12 @@ PP_API int pp_gen_run(pp_handle h, const int* frame_ids, const int* win_t, const
                       void* pred_f16, void* stream);
 PP_API int pp_gen_end(pp_handle h);
 /* uint8 composite with the reference's truncation / 0.5-0.5 blending order.  frame_ids / first_visit are
- * device int32 arrays of length l_t; orig / comp are uint8 [T][H][W][3]; masks float32 [T,1,H,W]. */
+ * device int32 arrays of length l_t; orig / comp are uint8 [T][H][W][3]; masks float32 [T,1,H,W].
+ * half_math = 1 reproduces the roundings of the reference's fp16="enable" mode ((pred+1)/2 and *255 evaluated in
+ * half precision before the uint8 truncation), 0 its fp32 mode. */
 PP_API int pp_composite(pp_handle h, const void* pred_f16, const float* masks_dilated, const uint8_t* orig, uint8_t* comp,
-                 const int* frame_ids_dev, const int* first_visit_dev, int l_t, int H, int W, void* stream);
+                 const int* frame_ids_dev, const int* first_visit_dev, int l_t, int H, int W, int half_math,
+                 void* stream);
 
 /* Device pre-processing when no resize is needed (reference utils/image_utils.py:106-197): image [T,H,W,3]
  * float 0..1 -> uint8 (truncate) [T,H,W,3] + frames [T,3,H,W] in [-1,1]; mask [mask_frames,H,W] float ->

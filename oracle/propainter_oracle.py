@@ -164,8 +164,8 @@ def raft_pairs(sd, img1, img2, iters, return_trace=False):
         corr = corr_lookup(pyr, coords1)
         net, mask, delta = raft_update(sd, net, inp, corr, coords1 - coords0)
         coords1 = coords1 + delta
-        if return_trace:
-            trace.append((coords1 - coords0).clone())
+        if return_trace:   # raft.py:141-147: flow_predictions holds the up-sampled flow of every iteration
+            trace.append(convex_upsample(coords1 - coords0, mask))
     up = convex_upsample(coords1 - coords0, mask)
     return (up, trace) if return_trace else up
 
@@ -631,6 +631,21 @@ def window_schedule(video_length, neighbor_length, ref_stride, subvideo_length):
     return sched
 
 
+def composite_window(comp, pred255, binary_masks, original_frames, neighbor_ids):
+    """The uint8 composite of one window (propainter_inference.py:294-307), in place on the list ``comp``.
+
+    pred255: [l_t,H,W,3] float array = ((pred+1)/2) * 255 in the dtype the reference holds at that point (float32 with
+    fp16="disable"; float16 with fp16="enable", where both the +1, /2 on the device and the numpy *255 round to half);
+    binary_masks: [l_t,H,W,1] uint8 dilated masks; original_frames: list of HxWx3 uint8."""
+    for i, idx in enumerate(neighbor_ids):
+        img = np.array(pred255[i]).astype(np.uint8) * binary_masks[i] + original_frames[idx] * (1 - binary_masks[i])
+        if comp[idx] is None:
+            comp[idx] = img
+        else:
+            comp[idx] = comp[idx].astype(np.float32) * 0.5 + img.astype(np.float32) * 0.5
+        comp[idx] = comp[idx].astype(np.uint8)
+
+
 def feature_propagation(gen_sd, updated_frames, updated_masks, masks_dilated, flows_bi, original_frames,
                         neighbor_length, ref_stride, subvideo_length):
     """feature_propagation incl. the host composite (propainter_inference.py:228-311)."""
@@ -643,13 +658,7 @@ def feature_propagation(gen_sd, updated_frames, updated_masks, masks_dilated, fl
                               masks_dilated[:, ids], updated_masks[:, ids], len(nb))
         pred = ((pred.view(-1, 3, H, W) + 1) / 2).cpu().permute(0, 2, 3, 1).numpy() * 255
         bm = masks_dilated[0, nb].cpu().permute(0, 2, 3, 1).numpy().astype(np.uint8)
-        for i, idx in enumerate(nb):
-            img = np.array(pred[i]).astype(np.uint8) * bm[i] + original_frames[idx] * (1 - bm[i])
-            if comp[idx] is None:
-                comp[idx] = img
-            else:
-                comp[idx] = comp[idx].astype(np.float32) * 0.5 + img.astype(np.float32) * 0.5
-            comp[idx] = comp[idx].astype(np.uint8)
+        composite_window(comp, pred, bm, original_frames, nb)
     return comp
 
 

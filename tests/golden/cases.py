@@ -60,3 +60,42 @@ def e2e_case():
     T, H, W = 8, 128, 160
     return dict(T=T, H=H, W=W, image=synthetic_clip(T, H, W, 51), mask=synthetic_mask(T, H, W),
                 ref_stride=3, neighbor_length=4, subvideo_length=80, raft_iter=3)
+
+
+# ---- round 2: cases on BASELINE.json's configs and on the branches the small cases above never take -----------
+
+NODE_DEFAULTS = dict(mask_dilates=5, flow_mask_dilates=8, ref_stride=10, neighbor_length=10, subvideo_length=80)
+
+
+def c1_case():
+    """BASELINE config[0]: 16 frames 320x180 -> processed at 320x176 (PIL bicubic resize), raft_iter=5, fp32 reference,
+    through the Inpaint node."""
+    T, H, W = 16, 180, 320
+    kw = dict(NODE_DEFAULTS, width=320, height=180, raft_iter=5, fp16="disable")
+    return dict(image=synthetic_clip(T, H, W, 61), mask=synthetic_mask(T, H, W), kwargs=kw)
+
+
+RAFT20_ITERS = (1, 5, 10, 15, 20)
+RAFT20_GAINS = {"damped": 0.15, "undamped": 1.3}
+
+
+def raft20_case():
+    """3 frames (2 pairs) at BASELINE's 640x360 for the raft_iter=20 error-growth test."""
+    return _clip(3, 360, 640, 71)
+
+
+def chunked_case():
+    """T > subvideo_length: drives the halo branches of complete_flow / image_propagation and the ref_num schedule
+    (reference propainter_inference.py:115-139, 172-209, 49-57)."""
+    T, H, W = 26, 128, 128
+    return dict(T=T, H=H, W=W, image=synthetic_clip(T, H, W, 81), mask=synthetic_mask(T, H, W),
+                ref_stride=3, neighbor_length=4, subvideo_length=12, raft_iter=2)
+
+
+def outpaint_case():
+    """Outpaint node: 8 frames 160x128, width_scale 1.2 -> canvas 192x128; token grid 11x16 is padded to 15x18 (both
+    axes), so this is also the padded-grid case."""
+    T, H, W = 8, 128, 160
+    kw = dict(width=160, height=128, width_scale=1.2, height_scale=1.0, mask_dilates=5, flow_mask_dilates=8,
+              ref_stride=3, neighbor_length=4, subvideo_length=80, raft_iter=3, fp16="disable")
+    return dict(image=synthetic_clip(T, H, W, 91), kwargs=kw)

@@ -254,16 +254,191 @@ def check_e2e(golden):
                 upd_frames=stats(uf.float(), torch.from_numpy(golden["e2e_updated_frames"])))
 
 
+# ------------------------------------------------------------------------------------------------ round 2
+def _psnr_stats(a, b, hole=None):
+    a, b = np.asarray(a).astype(np.float64), np.asarray(b).astype(np.float64)
+    mse = ((a - b) ** 2).mean()
+    out = dict(psnr=float(10 * np.log10(255 ** 2 / max(mse, 1e-12))), max_abs_u8=float(np.abs(a - b).max()),
+               frac_gt1=float((np.abs(a - b) > 1).mean()), frac_ne=float((a != b).mean()))
+    if hole is not None and hole.any():
+        mh = (((a - b) ** 2).sum(-1)[hole]).mean() / 3
+        out["psnr_hole"] = float(10 * np.log10(255 ** 2 / max(mh, 1e-12)))
+    return out
+
+
+def _node_models():
+    """The node classes find the synthetic-weight engine through model_utils.set_resident_models."""
+    from comfyui_propainter_nodes_b200.utils import model_utils as MU
+    m = full_models()
+    MU.set_resident_models(DEV, m)
+    return m
+
+
+def _img_u8(img):
+    return (img.detach().cpu().float().numpy() * 255.0 + 0.5).astype(np.uint8)
+
+
+def check_c1_node(golden2):
+    """BASELINE config[0] through ProPainterInpaint (320x180 -> 320x176 resize inside the node), fp16="disable"."""
+    from comfyui_propainter_nodes_b200.propainter_nodes import ProPainterInpaint
+    m = _node_models()
+    c = cases.c1_case()
+    img, fmask, dmask = ProPainterInpaint().propainter_inpainting(c["image"], c["mask"], **c["kwargs"])
+    torch.cuda.synchronize()
+    assert img.device.type == "cpu" and img.dtype == torch.float32
+    hole = golden2["c1_masks_dilated_u8"] > 0
+    st = _psnr_stats(_img_u8(img), golden2["c1_image_u8"], hole)
+    st["flow_masks_equal"] = bool(np.array_equal(_img_u8(fmask), golden2["c1_flow_masks_u8"]))
+    st["masks_dilated_equal"] = bool(np.array_equal(_img_u8(dmask), golden2["c1_masks_dilated_u8"]))
+    # stage tensors of the same run
+    kw = c["kwargs"]
+    T, H, W = c["image"].shape[:3]
+    icfg = IU.ImageConfig(kw["width"], kw["height"], kw["mask_dilates"], kw["flow_mask_dilates"], (W, H), T)
+    ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(c["image"]), c["mask"], icfg, torch.device(DEV))
+    cfg = PI.ProPainterConfig(kw["ref_stride"], kw["neighbor_length"], kw["subvideo_length"], kw["raft_iter"], kw["fp16"],
+                              T, torch.device(DEV), icfg.process_size)
+    gt = PI.compute_flow(m.raft_model, ft, cfg)
+    uf, um, pf = PI.process_inpainting(m, ft, fm, md, cfg)
+    st["raft_flow"] = stats(gt[0][..., ::2, ::2], torch.from_numpy(golden2["c1_gt_flow_f_s2"]).float())
+    st["pred_flow"] = stats(pf[0], torch.from_numpy(golden2["c1_pred_flow_f"]).float())
+    st["updated_masks_mismatch"] = float((_img_u8(um) != golden2["c1_updated_masks_u8"]).mean())
+    return st
+
+
+def check_raft20(golden2):
+    """20 GRU iterations at 640x360 against the fp32 reference, error vs iteration, damped and un-damped flow head."""
+    fr = cases.raft20_case()[0].to(DEV)
+    out = {}
+    for tag, gain in cases.RAFT20_GAINS.items():
+        eng = E.Engine(DEV, workspace_gb=6.0).load_weights(Wt.synthetic_raft_state_dict(flow_head_gain=gain),
+                                                           Wt.synthetic_rfc_state_dict(), Wt.synthetic_generator_state_dict())
+        for it in cases.RAFT20_ITERS:
+            ff, _ = eng.raft_bidir(fr, it)
+            torch.cuda.synchronize()
+            ref = torch.from_numpy(golden2[f"raft20_{tag}_it{it}_s4"])
+            s = stats(ff[:, :, ::4, ::4], ref)
+            d = (ff[:, :, ::4, ::4].cpu() - ref).abs().flatten()
+            s["p99_abs"] = float(torch.quantile(d, 0.99))
+            out[f"{tag}_it{it}"] = s
+            if it == max(cases.RAFT20_ITERS):
+                out[f"{tag}_final"] = stats(ff[:, :, ::2, ::2], torch.from_numpy(golden2[f"raft20_{tag}_final_s2"]))
+        eng.close()
+    return out
+
+
+def check_chunked(golden2):
+    """T=26 > subvideo_length=12: chunked complete_flow / image_propagation halos + ref_num schedule."""
+    m = full_models()
+    e = cases.chunked_case()
+    icfg = IU.ImageConfig(e["W"], e["H"], 5, 8, (e["W"], e["H"]), e["T"])
+    ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(e["image"]), e["mask"], icfg, torch.device(DEV))
+    cfg = PI.ProPainterConfig(e["ref_stride"], e["neighbor_length"], e["subvideo_length"], e["raft_iter"], "disable",
+                              e["T"], torch.device(DEV), icfg.process_size)
+    gt = PI.compute_flow(m.raft_model, ft, cfg)
+    uf, um, pf = PI.process_inpainting(m, ft, fm, md, cfg)
+    comp = PI.feature_propagation(m.inpaint_model, uf, um, md, pf, orig, cfg)
+    torch.cuda.synchronize()
+    hole = md[0, :, 0].cpu().numpy() > 0.5
+    st = _psnr_stats(np.stack(comp), golden2["chunk_frames_u8"], hole)
+    st["raft_flow"] = stats(gt[0][..., ::2, ::2], torch.from_numpy(golden2["chunk_gt_flow_f_s2"]).float())
+    st["pred_flow_f"] = stats(pf[0], torch.from_numpy(golden2["chunk_pred_flow_f"]).float())
+    st["pred_flow_b"] = stats(pf[1], torch.from_numpy(golden2["chunk_pred_flow_b"]).float())
+    st["updated_masks_mismatch"] = float((_img_u8(um) != golden2["chunk_updated_masks_u8"]).mean())
+    return st
+
+
+def check_outpaint_node(golden2):
+    from comfyui_propainter_nodes_b200.propainter_nodes import ProPainterOutpaint
+    _node_models()
+    o = cases.outpaint_case()
+    img, omask, ow, oh = ProPainterOutpaint().propainter_outpainting(o["image"], **o["kwargs"])
+    torch.cuda.synchronize()
+    hole = golden2["outpaint_mask_u8"] > 0
+    st = _psnr_stats(_img_u8(img), golden2["outpaint_image_u8"], hole)
+    st["mask_equal"] = bool(np.array_equal(_img_u8(omask), golden2["outpaint_mask_u8"]))
+    st["size_equal"] = [int(ow), int(oh)] == [int(v) for v in golden2["outpaint_size"]]
+    return st
+
+
+def check_composite_exact():
+    """pp_composite vs the numpy restatement of the reference loop on IDENTICAL predictions: byte for byte, in the
+    float32 mode and in the half mode, over a schedule with up to three visits per frame."""
+    eng = bare_engine()
+    g = torch.Generator().manual_seed(77)
+    T, H, W = 9, 40, 56
+    sched = O.window_schedule(T, 4, 3, 80)
+    orig = torch.randint(0, 256, (T, H, W, 3), generator=g, dtype=torch.uint8)
+    md = (torch.rand(T, 1, H, W, generator=g) > 0.4).float()
+    res = {}
+    for half in (False, True):
+        comp_ref = [None] * T
+        comp = torch.zeros_like(orig).to(DEV)
+        visited = [False] * T
+        for nb, _ in sched:
+            # tanh outputs incl. the exact ends and values whose *255 image sits next to an integer
+            pred = (torch.rand(len(nb), H, W, 4, generator=g) * 2 - 1).half()
+            pred[0, 0, :8, :3] = torch.tensor([-1.0, 1.0, 0.0, 0.5, -0.5, 0.9961, 0.00392, -0.00392]).half()[:, None]
+            p = pred[..., :3]
+            if half:   # the reference's fp16 mode: (pred + 1) / 2 in half on the device, numpy * 255 stays half
+                p255 = ((p + 1) / 2).numpy() * 255
+                assert p255.dtype == np.float16
+            else:      # fp32 mode, same prediction values
+                p255 = ((p.float() + 1) / 2).numpy() * 255
+            bm = md[nb].permute(0, 2, 3, 1).numpy().astype(np.uint8)
+            O.composite_window(comp_ref, p255, bm, [o.numpy() for o in orig], nb)
+            ids = torch.tensor(nb, dtype=torch.int32, device=DEV)
+            first = torch.tensor([0 if visited[i] else 1 for i in nb], dtype=torch.int32, device=DEV)
+            for i in nb:
+                visited[i] = True
+            eng.composite(pred.to(DEV), md.to(DEV), orig.to(DEV), comp, ids, first, half)
+        torch.cuda.synchronize()
+        res["half" if half else "float"] = int((comp.cpu().numpy() != np.stack(comp_ref)).sum())
+    return res
+
+
+def check_small_workspace_fallback():
+    """A workspace far below what one batched pass needs: gen_run splits the schedule into sub-batches (down to one
+    window) and the result is bit-identical; a failing call leaves the arena untouched (no leak)."""
+    m = full_models()
+    e = cases.e2e_case()
+    icfg = IU.ImageConfig(e["W"], e["H"], 5, 8, (e["W"], e["H"]), e["T"])
+    ft, fm, md, orig = IU.prepare_frames_and_masks(IU.convert_image_to_frames(e["image"]), e["mask"], icfg, torch.device(DEV))
+    cfg = PI.ProPainterConfig(e["ref_stride"], e["neighbor_length"], e["subvideo_length"], e["raft_iter"], "enable",
+                              e["T"], torch.device(DEV), icfg.process_size)
+    uf, um, pf = PI.process_inpainting(m, ft, fm, md, cfg)
+    ref = np.stack(PI.feature_propagation(m.inpaint_model, uf, um, md, pf, orig, cfg))
+    small = E.Engine(DEV, workspace_gb=0.3).load_weights(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
+                                                         Wt.synthetic_generator_state_dict())
+    ms = Models(StageHandle(small, "raft"), StageHandle(small, "flow"), StageHandle(small, "inpaint"))
+    sched = PI.window_schedule(cfg)
+    n_batches = len(small.gen_batches(sched, small.workspace.numel()))
+    out = np.stack(PI.feature_propagation(ms.inpaint_model, uf, um, md, pf, orig, cfg))
+    # an impossible request fails loudly and leaves the arena as it was
+    leaked = None
+    try:
+        small.raft_bidir(torch.zeros(3, 3, 1024, 2048, device=DEV), 1)
+    except RuntimeError as ex:
+        leaked = str(ex)
+    out2 = np.stack(PI.feature_propagation(ms.inpaint_model, uf, um, md, pf, orig, cfg))
+    small.close()
+    return dict(mismatch=int((out != ref).sum()), mismatch_after_failure=int((out2 != ref).sum()), sub_batches=n_batches,
+                failure=leaked)
+
+
 def main():
     import json
     import os
     golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+    golden2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs_r2.npz"))
     only = sys.argv[1:]
     checks = [(f"conv:{n}", (lambda n=n: check_conv(n))) for n in CONV_CASES]
     checks += [("corr_lookup", check_corr_lookup), ("imgprop_step", check_imgprop_step), ("attention", check_attention),
                ("raft", lambda: check_raft(golden)), ("rfc", lambda: check_rfc(golden)),
                ("imgprop", lambda: check_imgprop(golden)), ("window", lambda: check_window(golden)),
-               ("e2e", lambda: check_e2e(golden))]
+               ("e2e", lambda: check_e2e(golden)), ("c1_node", lambda: check_c1_node(golden2)),
+               ("raft20", lambda: check_raft20(golden2)), ("chunked", lambda: check_chunked(golden2)),
+               ("outpaint_node", lambda: check_outpaint_node(golden2)), ("composite_exact", check_composite_exact),
+               ("small_workspace", check_small_workspace_fallback)]
     for name, fn in checks:
         if only and not any(o in name for o in only):
             continue

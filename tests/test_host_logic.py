@@ -56,7 +56,7 @@ def test_build_layers_covers_checkpoints():
                                  Wt.synthetic_generator_state_dict())
     assert len(convs) == 150 and len(tens) == 8 * 6
     # every kernel-side input channel count is a multiple of 8
-    for name, (w, b, groups, cmap) in convs.items():
+    for name, (w, b, groups, cmap, macs) in convs.items():
         cin = len(cmap) if cmap is not None else w.shape[1]
         assert (cin + (-cin) % 8) % 8 == 0
     # GRU gate merge: z|r stacked along Cout
@@ -67,7 +67,7 @@ def test_bn_folding_matches_batchnorm():
     sd = {k[7:]: v for k, v in Wt.synthetic_raft_state_dict().items()}
     convs, _ = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
                               Wt.synthetic_generator_state_dict())
-    w, b, _, _ = convs["raft.cnet.layer1.0.conv1"]
+    w, b, _, _, _ = convs["raft.cnet.layer1.0.conv1"]
     x = torch.randn(1, 64, 9, 11)
     y = torch.nn.functional.conv2d(x, sd["cnet.layer1.0.conv1.weight"], sd["cnet.layer1.0.conv1.bias"], padding=1)
     y = torch.nn.functional.batch_norm(y, sd["cnet.layer1.0.norm1.running_mean"], sd["cnet.layer1.0.norm1.running_var"],
@@ -165,7 +165,7 @@ def test_encoder14_dense_weights_equal_grouped_conv():
     import torch.nn.functional as F
     sd = Wt.synthetic_generator_state_dict()
     convs, _ = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(), sd)
-    w_dense, b, groups, cmap = convs["gen.encoder.14"]
+    w_dense, b, groups, cmap, macs = convs["gen.encoder.14"]
     assert groups == 1 and cmap is None and tuple(w_dense.shape[:2]) == (256, 640)
     g = torch.Generator().manual_seed(11)
     x0, prev = torch.randn(1, 256, 9, 11, generator=g), torch.randn(1, 384, 9, 11, generator=g)
@@ -183,7 +183,7 @@ def test_pad64_layers_are_registered_with_zero_extended_channels():
     convs, _ = E.build_layers(Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
                               Wt.synthetic_generator_state_dict())
     for name in E.Engine.PAD64_CONVS:
-        w, b, groups, cmap = convs[name]
+        w, b, groups, cmap, _ = convs[name]
         cmap = list(cmap) if cmap is not None else list(range(w.shape[1]))
         padded = cmap + [-1] * ((-len(cmap)) % 64)
         assert groups == 1 and len(padded) % 64 == 0 and len(padded) - len(cmap) < 64
@@ -202,9 +202,9 @@ def test_bench_reference_arm_prints_one_json_line(monkeypatch, capfd):
     """bench.py contract: exactly one JSON line on stdout (everything else on stderr) with the agreed keys."""
     import json
     import bench
-    monkeypatch.setattr(bench, "cpu_sample", lambda n=3: (0.5, 6.0))
+    monkeypatch.setattr(bench, "cpu_sample", lambda n=3: (0.5, 6.0, "port", 8))
     monkeypatch.setattr(bench, "_OUT_FD", 1)
-    args = type("A", (), dict(gpus=1, steps=2, warmup=1))()
+    args = type("A", (), dict(gpus=1, steps=2, warmup=1, no_ref_cuda=True))()
     print("noise that must not reach the JSON consumer", file=__import__("sys").stderr)
     bench.run_reference(args, rank=0)
     out = capfd.readouterr().out.strip().splitlines()

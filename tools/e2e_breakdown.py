@@ -14,7 +14,7 @@ def main():
     models = MU.build_models(dev, Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
                              Wt.synthetic_generator_state_dict(), workspace_gb=64.0)
     eng = models.raft_model.engine
-    MU._CACHE[str(dev)] = models
+    MU.set_resident_models(dev, models)   # the node's initialize_models() returns the resident engine
     image, mask = B.synthetic_inputs()
     image, mask = image.pin_memory(), mask.pin_memory()
     P = B.PARAMS

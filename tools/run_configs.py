@@ -20,7 +20,7 @@ def main():
     dev = torch.device("cuda:0")
     models = MU.build_models(dev, Wt.synthetic_raft_state_dict(), Wt.synthetic_rfc_state_dict(),
                              Wt.synthetic_generator_state_dict(), workspace_gb=100.0)
-    MU._CACHE[str(dev)] = models
+    MU.set_resident_models(dev, models)   # the node's initialize_models() returns the resident engine
     common = dict(mask_dilates=5, flow_mask_dilates=8, ref_stride=10, neighbor_length=10, subvideo_length=80,
                   raft_iter=20, fp16="enable")
     cases = {
