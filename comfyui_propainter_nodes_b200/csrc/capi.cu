@@ -104,8 +104,12 @@ int pp_comm_destroy(pp_handle h) {
 int pp_comm_all_gather_rows(pp_handle h, void* buf, const long long* rows_per_member, size_t row_bytes, int first_rank,
                             int n_members, void* stream) {
   PP_HANDLE(h);
-  PP_REQUIRE(buf != nullptr && rows_per_member != nullptr && row_bytes > 0, "pp_comm_all_gather_rows: bad argument");
-  return pp_comm_all_gather_rows_impl(e, buf, rows_per_member, row_bytes, first_rank, n_members, as_stream(stream));
+  PP_REQUIRE(buf != nullptr && rows_per_member != nullptr && row_bytes > 0 && n_members >= 1,
+             "pp_comm_all_gather_rows: bad argument");
+  std::vector<long long> off(n_members, 0);
+  for (int m = 1; m < n_members; ++m) off[m] = off[m - 1] + rows_per_member[m - 1];
+  return pp_comm_all_gather_blocks_impl(e, buf, off.data(), rows_per_member, row_bytes, first_rank, n_members,
+                                        as_stream(stream));
 }
 
 int pp_register_conv(pp_handle h, const char* name, const void* w, const float* bias, int cout_g, int cout_g_pad,
@@ -153,7 +157,19 @@ int pp_flow_complete(pp_handle h, const float* flows_f, const float* flows_b, co
   PP_HANDLE(h);
   PP_REQUIRE(flows_f && flows_b && flow_masks && out_f && out_b, "pp_flow_complete: null pointer");
   ArenaGuard guard(e.arena);
-  return pp_stage_flow_complete(e, flows_f, flows_b, flow_masks, T, H, W, out_f, out_b, as_stream(stream));
+  return pp_stage_flow_complete(e, flows_f, flows_b, flow_masks, T, H, W, out_f, out_b, 0, 1, as_stream(stream));
+}
+
+int pp_flow_complete_dist(pp_handle h, const float* flows_f, const float* flows_b, const float* flow_masks, int T, int H,
+                          int W, float* out_f, float* out_b, int team_first, int team_size, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(flows_f && flows_b && flow_masks && out_f && out_b, "pp_flow_complete_dist: null pointer");
+  PP_REQUIRE(e.comm != nullptr || team_size <= 1, "pp_flow_complete_dist: pp_comm_init was not called");
+  PP_REQUIRE(team_first >= 0 && team_size >= 1 && team_first + team_size <= e.world,
+             "pp_flow_complete_dist: team [%d, %d) of %d ranks", team_first, team_first + team_size, e.world);
+  ArenaGuard guard(e.arena);
+  return pp_stage_flow_complete(e, flows_f, flows_b, flow_masks, T, H, W, out_f, out_b, team_first, team_size,
+                                as_stream(stream));
 }
 
 int pp_image_propagate(pp_handle h, const float* frames, const float* masks, const float* flows_f,

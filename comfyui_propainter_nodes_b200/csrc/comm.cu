@@ -106,11 +106,11 @@ int pp_comm_destroy_impl(PPEngine& e) {
   return PP_OK;
 }
 
-// buf holds sum(rows) rows of row_bytes; member m (global rank first_rank + m) owns rows
-// [sum(rows[0..m)), +rows[m]) and has filled them; afterwards every member holds all rows.  Ranks outside
-// [first_rank, first_rank + n_members) return immediately.
-int pp_comm_all_gather_rows_impl(PPEngine& e, void* buf, const long long* rows, size_t row_bytes, int first_rank,
-                                 int n_members, cudaStream_t st) {
+// Member m (global rank first_rank + m) owns rows [row_offset[m], row_offset[m] + rows[m]) of `buf` (row_bytes each) and
+// has filled them; afterwards every member holds every block.  Blocks may sit in any order and members may own nothing
+// (pure receivers).  Ranks outside [first_rank, first_rank + n_members) return immediately.
+int pp_comm_all_gather_blocks_impl(PPEngine& e, void* buf, const long long* row_offset, const long long* rows,
+                                   size_t row_bytes, int first_rank, int n_members, cudaStream_t st) {
   if (n_members <= 1) return PP_OK;
   PP_REQUIRE(e.comm != nullptr, "pp_comm_all_gather_rows: pp_comm_init was not called");
   PP_REQUIRE(first_rank >= 0 && first_rank + n_members <= e.world, "pp_comm_all_gather_rows: ranks [%d, %d) of %d",
@@ -119,19 +119,18 @@ int pp_comm_all_gather_rows_impl(PPEngine& e, void* buf, const long long* rows, 
   if (me < 0 || me >= n_members) return PP_OK;
   NcclApi* api = nccl_api();
   ncclComm_t comm = static_cast<ncclComm_t>(e.comm);
-  std::vector<size_t> off(n_members + 1, 0);
-  for (int m = 0; m < n_members; ++m) {
-    PP_REQUIRE(rows[m] >= 0, "pp_comm_all_gather_rows: negative row count");
-    off[m + 1] = off[m] + (size_t)rows[m] * row_bytes;
-  }
+  for (int m = 0; m < n_members; ++m)
+    PP_REQUIRE(rows[m] >= 0 && row_offset[m] >= 0, "pp_comm_all_gather_rows: negative block");
   uint8_t* base = static_cast<uint8_t*>(buf);
   PP_NCCL_CHECK(api, api->GroupStart());
   for (int m = 0; m < n_members; ++m) {
     if (m == me) continue;
     if (rows[me] > 0)
-      PP_NCCL_CHECK(api, api->Send(base + off[me], (size_t)rows[me] * row_bytes, ncclUint8, first_rank + m, comm, st));
+      PP_NCCL_CHECK(api, api->Send(base + (size_t)row_offset[me] * row_bytes, (size_t)rows[me] * row_bytes, ncclUint8,
+                                   first_rank + m, comm, st));
     if (rows[m] > 0)
-      PP_NCCL_CHECK(api, api->Recv(base + off[m], (size_t)rows[m] * row_bytes, ncclUint8, first_rank + m, comm, st));
+      PP_NCCL_CHECK(api, api->Recv(base + (size_t)row_offset[m] * row_bytes, (size_t)rows[m] * row_bytes, ncclUint8,
+                                   first_rank + m, comm, st));
   }
   PP_NCCL_CHECK(api, api->GroupEnd());
   e.launches++;

@@ -135,14 +135,14 @@ void pp_build_ring_indices(int nh, int nw, std::vector<int>& out);
 int pp_comm_unique_id_impl(void* out128);
 int pp_comm_init_impl(PPEngine& e, const void* unique_id, int rank, int world);
 int pp_comm_destroy_impl(PPEngine& e);
-int pp_comm_all_gather_rows_impl(PPEngine& e, void* buf, const long long* rows, size_t row_bytes, int first_rank,
-                                 int n_members, cudaStream_t st);
+int pp_comm_all_gather_blocks_impl(PPEngine& e, void* buf, const long long* row_offset, const long long* rows,
+                                   size_t row_bytes, int first_rank, int n_members, cudaStream_t st);
 
 // ---- stages ---------------------------------------------------------------------------------------
 int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int iters, float* flows_f, float* flows_b,
                   cudaStream_t st);
 int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows_b, const float* flow_masks, int T,
-                           int H, int W, float* out_f, float* out_b, cudaStream_t st);
+                           int H, int W, float* out_f, float* out_b, int team_first, int team_size, cudaStream_t st);
 int pp_stage_image_propagate(PPEngine& e, const float* frames, const float* masks, const float* flows_f,
                              const float* flows_b, int T, int H, int W, float* upd_frames, float* upd_masks,
                              cudaStream_t st);

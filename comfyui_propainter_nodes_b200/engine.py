@@ -40,6 +40,7 @@ _SIGNATURES = {
     "pp_set_conv_macs": (_I, [_VP, _CP, ctypes.c_double]),
     "pp_raft_bidir": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP]),
     "pp_flow_complete": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
+    "pp_flow_complete_dist": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _I, _I, _VP]),
     "pp_image_propagate": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP, _VP, _VP]),
     "pp_gen_begin": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "pp_gen_begin_subset": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, ctypes.c_char_p, _VP]),
@@ -428,6 +429,18 @@ class Engine:
         of, ob = torch.empty_like(flows_f), torch.empty_like(flows_b)
         self._check(self.lib.pp_flow_complete(self.h, _ptr(flows_f), _ptr(flows_b), _ptr(flow_masks), T, H, W, _ptr(of),
                                               _ptr(ob), self._stream()))
+        return of, ob
+
+    def flow_complete_dist(self, flows_f, flows_b, flow_masks, team_first: int, team_size: int, out=None):
+        """Collective flow completion of one chunk by the ranks [team_first, team_first + team_size) (see
+        pp_flow_complete_dist); every team member gets the full completed flows."""
+        flows_f, flows_b, flow_masks = self._f32(flows_f), self._f32(flows_b), self._f32(flow_masks)
+        T, _, H, W = flow_masks.shape
+        assert flows_f.shape[0] == T - 1
+        of, ob = out if out is not None else (torch.empty_like(flows_f), torch.empty_like(flows_b))
+        assert of.is_contiguous() and ob.is_contiguous() and of.dtype == torch.float32
+        self._check(self.lib.pp_flow_complete_dist(self.h, _ptr(flows_f), _ptr(flows_b), _ptr(flow_masks), T, H, W,
+                                                   _ptr(of), _ptr(ob), int(team_first), int(team_size), self._stream()))
         return of, ob
 
     def image_propagate(self, frames, masks, flows_f, flows_b):

@@ -157,12 +157,65 @@ def inpaint_clip_distributed(models, frames, flow_masks, masks_dilated, orig_u8,
     return comp
 
 
+def flow_chunks(n_flows: int, subvideo_length: int, pad: int = 5):
+    """The reference's chunking of complete_flow (propainter_inference.py:115-139): [(f0, f1, s, e)] = flows [f0, f1)
+    are produced from the padded range [s, e) (masks [s, e])."""
+    if n_flows <= subvideo_length:
+        return [(0, n_flows, 0, n_flows)]
+    out = []
+    for f in range(0, n_flows, subvideo_length):
+        f1 = min(n_flows, f + subvideo_length)
+        out.append((f, f1, max(0, f - pad), min(n_flows, f1 + pad)))
+    return out
+
+
+def flow_teams(n_chunks: int, world: int):
+    """Ranks -> teams for flow completion: as many chunks in flight as possible (the recurrence inside a chunk is
+    serial, so chunk-level parallelism comes first), the ranks of a team then split directions and frames of ONE
+    chunk.  Returns (n_teams, team_size); team k = ranks [k*team_size, (k+1)*team_size), left-over ranks idle."""
+    n_teams = max(1, min(n_chunks, world))
+    return n_teams, world // n_teams
+
+
 def complete_flow_distributed(flow_model, flows_bi, flow_masks, subvideo_length, rank, world, group=None):
-    """Flow completion of one clip on `world` ranks.  The recurrence is serial in time, so what shards is
-    (a) the independent (sub-video chunk, direction) passes and (b) inside a pass the per-frame encoder / decoder.
-    This first version computes every pass on every rank (no exchange); Engine.flow_complete_dist replaces it."""
-    from . import propainter_inference as PI
+    """Flow completion of one clip on `world` ranks (every rank holds the full inputs, every rank gets the full
+    result).  The recurrence is serial in time, so what shards is (a) the independent sub-video chunks -> teams of
+    ranks, (b) inside a chunk the two direction passes and the per-frame encoder / decoder (pp_flow_complete_dist).
+    Exchange: the in-team all-gathers of the C call, then one all-gather of the chunks between teams."""
     eng = flow_model.engine
-    if hasattr(eng, "flow_complete_dist") and getattr(eng, "world", 1) > 1:
-        return PI.complete_flow(flow_model, flows_bi, flow_masks, subvideo_length, distributed=True)
-    return PI.complete_flow(flow_model, flows_bi, flow_masks, subvideo_length)
+    ff, fb, fm = flows_bi[0][0], flows_bi[1][0], flow_masks[0]
+    dt = flows_bi[0].dtype
+    L = ff.shape[0]
+    if getattr(eng, "world", 1) <= 1:      # no engine communicator (CPU/gloo logic tests): every rank computes all
+        from . import propainter_inference as PI
+        return PI.complete_flow(flow_model, flows_bi, flow_masks, subvideo_length)
+    chunks = flow_chunks(L, subvideo_length)
+    n_teams, tsize = flow_teams(len(chunks), world)
+    team = rank // tsize if rank < n_teams * tsize else -1
+    of = torch.empty(L, 2, ff.shape[-2], ff.shape[-1], device=eng.device, dtype=torch.float32)
+    ob = torch.empty_like(of)
+    ff32, fb32, fm32 = eng._f32(ff), eng._f32(fb), eng._f32(fm)
+    for r0 in range(0, len(chunks), n_teams):
+        ci = r0 + team
+        if team < 0 or ci >= len(chunks):
+            continue
+        f0, f1, s, e = chunks[ci]
+        a, b = eng.flow_complete_dist(ff32[s:e], fb32[s:e], fm32[s:e + 1], team * tsize, tsize)
+        of[f0:f1] = a[f0 - s:f1 - s]
+        ob[f0:f1] = b[f0 - s:f1 - s]
+    if n_teams > 1 or n_teams * tsize < world:
+        # chunk ci lives on every rank of team ci % n_teams; its first rank feeds the others
+        # one gather per round: in round r team k's leader owns chunk r*n_teams + k
+        for r0 in range(0, len(chunks), n_teams):
+            rows = [0] * world
+            for k in range(n_teams):
+                if r0 + k < len(chunks):
+                    f0, f1, _, _ = chunks[r0 + k]
+                    rows[k * tsize] = f1 - f0
+            # blocks of one round are consecutive chunks: cumulative placement relative to the round's first row
+            base = chunks[r0][0]
+            n_rows = sum(rows)
+            for t in (of, ob):
+                view = t[base:base + n_rows]
+                eng.comm_all_gather_rows(view, rows, 0)
+    return of.unsqueeze(0).to(dt), ob.unsqueeze(0).to(dt)

@@ -75,6 +75,13 @@ PP_API int pp_raft_bidir(pp_handle h, const float* frames, int T, int H, int W, 
 /* flows [T-1,2,H,W], flow_masks [T,1,H,W]  ->  completed flows [T-1,2,H,W] (prediction inside the mask). */
 PP_API int pp_flow_complete(pp_handle h, const float* flows_f, const float* flows_b, const float* flow_masks, int T, int H,
                      int W, float* out_f, float* out_b, void* stream);
+/* The same call made collectively by the ranks [team_first, team_first + team_size) of the communicator on the same
+ * (replicated) inputs; ranks outside the team return at once.  The two direction passes go to the two halves of the
+ * team, the per-frame encoder / decoder is sharded inside a half (encoder with the +-8-frame temporal halo), the
+ * serial recurrence runs on every rank of its half; NCCL all-gathers of the encoder features (inside a half) and of
+ * the completed flows (whole team) leave the full result on every rank of the team.  team_size 1 = pp_flow_complete. */
+PP_API int pp_flow_complete_dist(pp_handle h, const float* flows_f, const float* flows_b, const float* flow_masks, int T,
+                                 int H, int W, float* out_f, float* out_b, int team_first, int team_size, void* stream);
 /* frames [T,3,H,W], masks [T,1,H,W], completed flows  ->  updated frames [T,3,H,W], updated masks [T,1,H,W]. */
 PP_API int pp_image_propagate(pp_handle h, const float* frames, const float* masks, const float* flows_f,
                        const float* flows_b, int T, int H, int W, float* updated_frames, float* updated_masks,

@@ -70,3 +70,27 @@ def test_all_gather_variable_world2_gloo():
     port = 29500 + (os.getpid() % 500)
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert ret.get(0) and ret.get(1)
+
+
+def test_flow_chunks_and_teams():
+    """Chunking of complete_flow equals the reference's loop (propainter_inference.py:115-139); teams cover the ranks."""
+    assert P.flow_chunks(79, 80) == [(0, 79, 0, 79)]
+    ch = P.flow_chunks(239, 80)
+    assert ch == [(0, 80, 0, 85), (80, 160, 75, 165), (160, 239, 155, 239)]
+    for L, sub in ((25, 12), (29, 10), (239, 80), (100, 100), (101, 100)):
+        got = P.flow_chunks(L, sub)
+        ref = []
+        if L <= sub:
+            ref = [(0, L, 0, L)]
+        else:
+            for f in range(0, L, sub):          # the reference's index arithmetic
+                s_f, e_f = max(0, f - 5), min(L, f + sub + 5)
+                pad_s, pad_e = max(0, f) - s_f, e_f - min(L, f + sub)
+                ref.append((s_f + pad_s, e_f - pad_e, s_f, e_f))
+        assert got == ref, (L, sub)
+        assert [c[0] for c in got][1:] == [c[1] for c in got][:-1] and got[-1][1] == L
+    for n_chunks in (1, 2, 3, 7):
+        for world in (1, 2, 3, 4, 8):
+            n_teams, size = P.flow_teams(n_chunks, world)
+            assert 1 <= n_teams <= n_chunks and size >= 1 and n_teams * size <= world
+    assert P.flow_teams(1, 8) == (1, 8) and P.flow_teams(3, 8) == (3, 2) and P.flow_teams(3, 2) == (2, 1)
