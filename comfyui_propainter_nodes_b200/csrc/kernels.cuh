@@ -36,6 +36,8 @@ int pp_k_convex_upsample(const float* coords1, const __half* mask, float* out_nc
 // ---- propagation (kernels_prop.cu) --------------------------------------------------------------
 int pp_k_imgprop_step(const __half* cur, const __half* prop_in, __half* prop_out, const __half* flow_prop,
                       const __half* flow_check, int H, int W, cudaStream_t st);
+int pp_k_imgprop_run(const __half* in4, __half* bwd, __half* fwd, const __half* ff, const __half* fbk,
+                     const float* masks, int T, int H, int W, int* scratch, cudaStream_t st);
 int pp_k_imgprop_pack(const float* frames, const float* masks, __half* dst, int T, int H, int W, cudaStream_t st);
 int pp_k_imgprop_finish(const __half* prop, const float* frames, const float* masks, float* upd_frames,
                         float* upd_masks, int T, int H, int W, cudaStream_t st);

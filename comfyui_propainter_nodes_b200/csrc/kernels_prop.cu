@@ -98,6 +98,157 @@ __global__ void imgprop_step(const uint2* __restrict__ cur, const uint2* __restr
   prop_out[idx] = o;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The whole bidirectional propagation (2(T-1) serial steps) as ONE persistent kernel.
+//
+// A step only changes pixels whose current mask is set: for m_cur = 0 the blend weight u and the new mask are 0 and
+// the output is the current pixel (model/propainter.py:186-196).  So the kernel works on the bounding box of the
+// hole (union over the clip, computed on the device), with `bwd` and `fwd` pre-initialised to the packed input, and
+// a grid-wide barrier between steps replaces 158 kernel launches.  Everything that does not depend on the
+// previous step (current pixel, both flows, the fb-consistency test, the sampling positions) is fetched for step
+// s+1 before the barrier of step s, so the serial chain per step is one barrier + one gather from L2.
+// ------------------------------------------------------------------------------------------------
+struct PropPre {        // the step-independent half of one pixel's work
+  int pix;              // pixel index in the frame, -1: nothing to do
+  int near;             // nearest texel index of the propagated frame or -1
+  int x0, y0;
+  float w00, w01, w10, w11;
+  float valid;
+  uint2 cur;
+};
+
+__device__ __forceinline__ PropPre prop_pre(const uint2* __restrict__ cur, const __half2* __restrict__ flow_prop,
+                                            const __half2* __restrict__ flow_check, int pix, int H, int W, bool cur_is_input) {
+  PropPre r;
+  r.pix = pix;
+  r.near = -1;
+  r.cur = cur_is_input ? __ldg(&cur[pix]) : __ldcg(&cur[pix]);
+  const float mcur = __half2float(reinterpret_cast<const __half*>(&r.cur)[3]);
+  r.valid = 0.f; r.x0 = r.y0 = 0; r.w00 = r.w01 = r.w10 = r.w11 = 0.f;
+  if (mcur == 0.f) { r.near = -2; return r; }          // -2: pass-through pixel
+  const int x = pix % W, y = pix / W;
+  const float2 fp = __half22float2(__ldg(&flow_prop[pix]));
+  const float sx = sample_coord((float)x + fp.x, W), sy = sample_coord((float)y + fp.y, H);
+  const Bilin b = bilin_setup(sx, sy, W, H);
+  r.valid = fb_valid(fp, sample_flow2(flow_check, b, W));
+  const int nx = (int)nearbyintf(sx), ny = (int)nearbyintf(sy);
+  if (nx >= 0 && nx < W && ny >= 0 && ny < H) r.near = ny * W + nx;
+  r.x0 = b.x0; r.y0 = b.y0; r.w00 = b.w00; r.w01 = b.w01; r.w10 = b.w10; r.w11 = b.w11;
+  return r;
+}
+
+__device__ __forceinline__ uint2 prop_post(const PropPre& r, const uint2* prop_in, int W) {
+  float wr = 0.f, wg = 0.f, wb = 0.f;
+  if (r.near >= 0) {
+    const uint2 t = __ldcg(&prop_in[r.near]);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    wr = a.x; wg = a.y; wb = c.x;
+  }
+  float mw = 0.f;
+  auto mk = [&](int i) { const uint2 t = __ldcg(&prop_in[i]); return __half2float(reinterpret_cast<const __half*>(&t)[3]); };
+  if (r.w00 != 0.f) mw += r.w00 * mk(r.y0 * W + r.x0);
+  if (r.w01 != 0.f) mw += r.w01 * mk(r.y0 * W + r.x0 + 1);
+  if (r.w10 != 0.f) mw += r.w10 * mk((r.y0 + 1) * W + r.x0);
+  if (r.w11 != 0.f) mw += r.w11 * mk((r.y0 + 1) * W + r.x0 + 1);
+  const float mv = mw > 0.1f ? 1.f : 0.f;
+  const float2 c01 = __half22float2(*reinterpret_cast<const __half2*>(&r.cur.x));
+  const float2 c23 = __half22float2(*reinterpret_cast<const __half2*>(&r.cur.y));
+  const float mcur = c23.y;
+  const float u = (mcur * r.valid * (1.f - mv)) > 0.1f ? 1.f : 0.f;
+  const float mnew = (mcur * (1.f - r.valid * (1.f - mv))) > 0.1f ? 1.f : 0.f;
+  uint2 o;
+  *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(u * wr + (1.f - u) * c01.x, u * wg + (1.f - u) * c01.y);
+  *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(u * wb + (1.f - u) * c23.x, mnew);
+  return o;
+}
+
+// bbox = {x0, y0, x1, y1} (inclusive) of mask > 0 over all frames; initialised to {W, H, -1, -1}
+__global__ void mask_bbox(const float* __restrict__ masks, long long total, int HW, int W, int* __restrict__ bbox) {
+  int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (masks[i] != 0.f) {
+      const int p = (int)(i % HW), x = p % W, y = p / W;
+      x0 = min(x0, x); y0 = min(y0, y); x1 = max(x1, x); y1 = max(y1, y);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+    x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if ((threadIdx.x & 31) == 0 && x1 >= 0) {
+    atomicMin(&bbox[0], x0); atomicMin(&bbox[1], y0); atomicMax(&bbox[2], x1); atomicMax(&bbox[3], y1);
+  }
+}
+
+__global__ void __launch_bounds__(256) imgprop_persistent(const uint2* __restrict__ in4, uint2* bwd, uint2* fwd,
+                                                          const __half2* __restrict__ ff, const __half2* __restrict__ fbk,
+                                                          int T, int H, int W, const int* __restrict__ bbox,
+                                                          unsigned int* counter) {
+  const int bx0 = bbox[0], by0 = bbox[1], bw = bbox[2] - bbox[0] + 1, bh = bbox[3] - bbox[1] + 1;
+  if (bbox[2] < 0) return;                                  // no hole anywhere: outputs are the pre-copied inputs
+  const int npix = bw * bh;
+  const int nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long HW = (long long)H * W;
+  const int steps = 2 * (T - 1);
+  auto bufs = [&](int s, const uint2*& cur, const uint2*& pin, uint2*& out, const __half2*& fprop, const __half2*& fchk) {
+    if (s < T - 1) {          // backward pass: idx = T-2 .. 0, prop flow = forward flow, check = backward flow
+      const int idx = T - 2 - s;
+      cur = in4 + idx * HW; pin = bwd + (idx + 1) * HW; out = bwd + idx * HW; fprop = ff + idx * HW; fchk = fbk + idx * HW;
+    } else {                  // forward pass over the backward pass's outputs: idx = 1 .. T-1
+      const int idx = s - (T - 1) + 1;
+      cur = bwd + idx * HW; pin = fwd + (idx - 1) * HW; out = fwd + idx * HW; fprop = fbk + (idx - 1) * HW; fchk = ff + (idx - 1) * HW;
+    }
+  };
+  auto pixel_of = [&](int j) { return (by0 + j / bw) * W + bx0 + j % bw; };
+  const uint2 *cur, *pin;
+  uint2* out;
+  const __half2 *fprop, *fchk;
+  PropPre pre;
+  pre.pix = -1;
+  if (gtid < npix) {
+    bufs(0, cur, pin, out, fprop, fchk);
+    pre = prop_pre(cur, fprop, fchk, pixel_of(gtid), H, W, true);
+  }
+  for (int s = 0; s < steps; ++s) {
+    bufs(s, cur, pin, out, fprop, fchk);
+    const bool fwd_pass = s >= T - 1;
+    // first pixel of this thread: its step-independent half was fetched before the previous barrier
+    if (pre.pix >= 0) {
+      if (pre.near != -2) {
+        const uint2 o = prop_post(pre, pin, W);
+        out[pre.pix] = o;
+        if (s == T - 2) fwd[pre.pix] = o;                   // frame 0 of the forward pass is the backward result
+      } else if (fwd_pass) {
+        out[pre.pix] = pre.cur;                             // pass-through (backward pass: already the pre-copied input)
+      } else if (s == T - 2) {
+        fwd[pre.pix] = pre.cur;
+      }
+    }
+    for (int j = gtid + nthreads; j < npix; j += nthreads) {   // holes larger than the grid: remaining pixels
+      const PropPre q = prop_pre(cur, fprop, fchk, pixel_of(j), H, W, !fwd_pass);
+      if (q.near != -2) {
+        const uint2 o = prop_post(q, pin, W);
+        out[q.pix] = o;
+        if (s == T - 2) fwd[q.pix] = o;
+      } else if (fwd_pass) {
+        out[q.pix] = q.cur;
+      } else if (s == T - 2) {
+        fwd[q.pix] = q.cur;
+      }
+    }
+    if (s + 1 < steps && gtid < npix) {
+      const uint2 *c2, *p2;
+      uint2* o2;
+      const __half2 *f2, *k2;
+      bufs(s + 1, c2, p2, o2, f2, k2);
+      // in the forward pass `cur` is a backward-pass output of THIS thread (same pixel mapping), complete by now
+      pre = prop_pre(c2, f2, k2, pixel_of(gtid), H, W, s + 1 < T - 1);
+    }
+    ppx::grid_barrier(counter, (unsigned)(s + 1) * gridDim.x);
+  }
+}
+
 // frames [T,3,H,W] f32 (already multiplied by (1-mask) here) + masks -> [T][H][W][4] fp16
 __global__ void imgprop_pack(const float* __restrict__ frames, const float* __restrict__ masks,
                              uint2* __restrict__ dst, long long HW, long long total) {
@@ -351,6 +502,36 @@ int pp_k_imgprop_step(const __half* cur, const __half* prop_in, __half* prop_out
       reinterpret_cast<const uint2*>(cur), reinterpret_cast<const uint2*>(prop_in), reinterpret_cast<uint2*>(prop_out),
       reinterpret_cast<const __half2*>(flow_prop), reinterpret_cast<const __half2*>(flow_check), H, W);
   PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+// bwd / fwd must hold copies of in4; scratch = 8 ints (bbox[4], barrier counter, pad)
+int pp_k_imgprop_run(const __half* in4, __half* bwd, __half* fwd, const __half* ff, const __half* fbk,
+                     const float* masks, int T, int H, int W, int* scratch, cudaStream_t st) {
+  static int grid_max = 0;
+  if (grid_max == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    PP_CUDA_CHECK(cudaGetDevice(&dev));
+    PP_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, imgprop_persistent, 256, 0));
+    PP_REQUIRE(per_sm >= 1, "imgprop: persistent kernel does not fit an SM");
+    grid_max = sms * (per_sm < 2 ? per_sm : 2);
+  }
+  const int init[8] = {W, H, -1, -1, 0, 0, 0, 0};
+  PP_CUDA_CHECK(cudaMemcpyAsync(scratch, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const long long total = (long long)T * H * W;
+  const long long want = (total + 256 * 16 - 1) / (256 * 16);
+  mask_bbox<<<(int)(want < 1184 ? want : 1184), 256, 0, st>>>(masks, total, H * W, W, scratch);
+  PP_CUDA_CHECK(cudaGetLastError());
+  const uint2* a0 = reinterpret_cast<const uint2*>(in4);
+  uint2* a1 = reinterpret_cast<uint2*>(bwd);
+  uint2* a2 = reinterpret_cast<uint2*>(fwd);
+  const __half2* a3 = reinterpret_cast<const __half2*>(ff);
+  const __half2* a4 = reinterpret_cast<const __half2*>(fbk);
+  const int* a8 = scratch;
+  unsigned int* a9 = reinterpret_cast<unsigned int*>(scratch + 4);
+  void* args[] = {&a0, &a1, &a2, &a3, &a4, &T, &H, &W, &a8, &a9};
+  PP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)imgprop_persistent, dim3(grid_max), dim3(256), args, 0, st));
   return PP_OK;
 }
 

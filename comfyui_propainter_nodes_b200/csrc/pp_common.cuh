@@ -91,6 +91,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------ grid-wide barrier (persistent kernels)
+// All CTAs of a co-resident grid (cooperative launch) meet here: `counter` counts arrivals since it was zeroed, the
+// k-th barrier of a kernel passes when it reaches k * gridDim.x.  Writes made before the barrier by any thread of the
+// grid are visible to every thread after it (read them with ld.global.cg / __ldcg: L1 is not coherent across SMs).
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ async copies
 // 16-byte cp.async (LDGSTS) with zero-fill when src_bytes == 0.
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {

@@ -262,29 +262,20 @@ int pp_stage_image_propagate(PPEngine& e, const float* frames, const float* mask
   PP_TRY(pp_k_flow_to_nhwc2(flows_f, ff, T - 1, H, W, st));
   PP_TRY(pp_k_flow_to_nhwc2(flows_b, fbk, T - 1, H, W, st));
   e.launches += 3;
-  const size_t fs = (size_t)HW * 4, ws = (size_t)HW * 2;
-  // backward pass: idx = T-1..0, prop flow = flows_forward[idx], check flow = flows_backward[idx]
-  PP_CUDA_CHECK(cudaMemcpyAsync(bwd + (size_t)(T - 1) * fs, in4 + (size_t)(T - 1) * fs, fs * sizeof(__half),
-                                cudaMemcpyDeviceToDevice, st));
-  for (int idx = T - 2; idx >= 0; --idx) {
-    {
-      // algorithmic bytes per pixel: cur 8 + propagated gather 8 + out 8 + 2 flows x 4 (32 B/px)
-      PPProfScope ps(e, "imgprop_step", (double)HW, 0.0, (double)HW * 32, st);
-      PP_TRY(pp_k_imgprop_step(in4 + idx * fs, bwd + (idx + 1) * fs, bwd + idx * fs, ff + idx * ws, fbk + idx * ws, H,
-                               W, st));
-    }
-    e.launches++;
+  // both passes in one persistent kernel (kernels_prop.cu): bwd / fwd start as copies of the packed input, only the
+  // pixels inside the hole's bounding box are touched by the 2(T-1) serial steps
+  const size_t all = (size_t)T * HW * 4 * sizeof(__half);
+  PP_CUDA_CHECK(cudaMemcpyAsync(bwd, in4, all, cudaMemcpyDeviceToDevice, st));
+  PP_CUDA_CHECK(cudaMemcpyAsync(fwd, in4, all, cudaMemcpyDeviceToDevice, st));
+  int* scratch;
+  PP_TRY(pp_alloc(e, &scratch, 8, "imgprop scratch"));
+  {
+    // algorithmic bytes of the reference's 2(T-1) steps (32 B per pixel and step); the kernel itself
+    // moves far less (hole pixels only + the two up-front copies)
+    PPProfScope ps(e, "imgprop", (double)HW * 2 * (T - 1), 0.0, (double)HW * 32 * 2 * (T - 1), st);
+    PP_TRY(pp_k_imgprop_run(in4, bwd, fwd, ff, fbk, masks, T, H, W, scratch, st));
   }
-  // forward pass over the backward pass's outputs: prop flow = flows_backward[idx-1], check = flows_forward[idx-1]
-  PP_CUDA_CHECK(cudaMemcpyAsync(fwd, bwd, fs * sizeof(__half), cudaMemcpyDeviceToDevice, st));
-  for (int idx = 1; idx < T; ++idx) {
-    {
-      PPProfScope ps(e, "imgprop_step", (double)HW, 0.0, (double)HW * 32, st);
-      PP_TRY(pp_k_imgprop_step(bwd + idx * fs, fwd + (idx - 1) * fs, fwd + idx * fs, fbk + (idx - 1) * ws,
-                               ff + (idx - 1) * ws, H, W, st));
-    }
-    e.launches++;
-  }
+  e.launches += 4;
   PP_TRY(pp_k_imgprop_finish(fwd, frames, masks, upd_frames, upd_masks, T, H, W, st));
   e.launches++;
   e.arena.release(mark0);
