@@ -61,6 +61,11 @@ int pp_create(int device, void* workspace, size_t workspace_bytes, pp_handle* ou
   e->device = device;
   e->arena.base = static_cast<uint8_t*>(workspace);
   e->arena.cap = workspace_bytes;
+  if (cudaMalloc(&e->prog_counter, 256) != cudaSuccess || cudaMemset(e->prog_counter, 0, 256) != cudaSuccess) {
+    delete e;
+    pp_set_error("pp_create: cudaMalloc of the program barrier word failed");
+    return PP_ERR_CUDA;
+  }
   *out = reinterpret_cast<pp_handle>(e);
   return PP_OK;
 }
@@ -79,8 +84,10 @@ int pp_set_workspace(pp_handle h, void* workspace, size_t workspace_bytes) {
 
 int pp_destroy(pp_handle h) {
   if (h != nullptr) {
-    pp_comm_destroy_impl(*reinterpret_cast<PPEngine*>(h));
-    delete reinterpret_cast<PPEngine*>(h);
+    PPEngine* e = reinterpret_cast<PPEngine*>(h);
+    pp_comm_destroy_impl(*e);
+    if (e->prog_counter != nullptr) cudaFree(e->prog_counter);
+    delete e;
   }
   return PP_OK;
 }
@@ -241,6 +248,38 @@ int pp_preprocess(pp_handle h, const float* image, const float* mask, int mask_f
   PP_TRY(pp_k_prepare_masks(mask, mask_frames, T, H, W, flow_mask_dilates, mask_dilates, scratch, flow_masks,
                             masks_dilated, as_stream(stream)));
   e.launches += 4;
+  return PP_OK;
+}
+
+int pp_preprocess_resize(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
+                         int out_h, int out_w, int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8, float* frames,
+                         float* flow_masks, float* masks_dilated, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(image && mask && orig_u8 && frames && flow_masks && masks_dilated, "pp_preprocess_resize: null pointer");
+  PP_REQUIRE(out_h > 0 && out_w > 0 && H > 0 && W > 0, "pp_preprocess_resize: bad size");
+  ArenaGuard guard(e.arena);
+  cudaStream_t st = as_stream(stream);
+  const size_t in_px = (size_t)T * H * W, mid_px = (size_t)T * H * out_w;
+  uint8_t *u8_in, *tmp, *m_in, *m_out;
+  int* coef;
+  const int mx = out_h > out_w ? out_h : out_w;
+  const double sc = fmax(fmax((double)H / out_h, (double)W / out_w), 1.0);
+  const size_t coef_ints = 2 * (size_t)mx * ((size_t)ceil(2.0 * sc) * 2 + 1 + 2) + 64;
+  PP_TRY(pp_alloc(e, &u8_in, in_px * 3, "resize input"));
+  PP_TRY(pp_alloc(e, &tmp, mid_px * 3, "resize pass 1"));
+  PP_TRY(pp_alloc(e, &m_in, (size_t)mask_frames * H * W, "mask input"));
+  PP_TRY(pp_alloc(e, &m_out, (size_t)mask_frames * out_h * out_w, "mask resized"));
+  PP_TRY(pp_alloc(e, &coef, coef_ints, "resize coefficients"));
+  // frames: float -> uint8 (truncate) -> bicubic -> originals + [-1,1] tensor (image_utils.py:106-114, 98-103, 186-190)
+  PP_TRY(pp_k_quantize_u8(image, u8_in, (long long)in_px * 3, st));
+  PP_TRY(pp_k_resize_bicubic_u8(u8_in, orig_u8, tmp, coef, coef_ints, T, H, W, 3, out_h, out_w, st));
+  PP_TRY(pp_k_u8_to_frames(orig_u8, frames, T, out_h, out_w, st));
+  // masks: float -> 8-bit 'L' image -> bicubic -> any non-zero -> dilations (image_utils.py:128-170)
+  PP_TRY(pp_k_quantize_u8(mask, m_in, (long long)mask_frames * H * W, st));
+  PP_TRY(pp_k_resize_bicubic_u8(m_in, m_out, tmp, coef, coef_ints, mask_frames, H, W, 1, out_h, out_w, st));
+  PP_TRY(pp_k_dilate_masks_u8(m_out, mask_frames, T, out_h, out_w, flow_mask_dilates, mask_dilates, flow_masks,
+                              masks_dilated, st));
+  e.launches += 9;
   return PP_OK;
 }
 

@@ -21,8 +21,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <memory>
+
 #include "conv_epilogue.cuh"
 #include "conv_igemm.cuh"
+#include "dcn_sample.cuh"
 
 namespace {
 
@@ -383,6 +386,301 @@ __global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_
   if (warp == W_MMA) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-layer program: up to PROG_MAX_LAYERS dependent layers (stride-1 convolutions of the kind above, and modulated
+// deformable sampling) executed by ONE launch of one CTA per SM, with a grid-wide barrier between consecutive layers.
+// The recurrent propagation steps of flow completion are 8 dependent layers over 3,600-7,200 pixels: as separate
+// launches each pays launch + prologue + pipeline fill/drain (~15-30 us, mostly fixed); here the fixed cost per layer
+// is one barrier (an atomic counter in global memory) and one TMA round trip, the weight producer runs ahead across the
+// barrier, and TMEM / mbarriers / tensor maps are set up once.
+//
+// Ordering between layers: the epilogue threads (the only writers of global memory) make their generic-proxy stores
+// visible to the async proxy (fence.proxy.async.global), meet on a named barrier, and one thread publishes the CTA's
+// arrival (threadfence + atomicAdd).  The TMA producer and the epilogue warps of the next layer spin on the counter
+// (ld.acquire.gpu) before they touch that layer's inputs; the producer adds the consumer-side proxy fence before
+// issuing TMA loads.  All 148 CTAs are co-resident (1 CTA per SM by shared memory), so the spin cannot deadlock.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PROG_MAX_LAYERS = 10;
+enum { PROG_CONV = 0, PROG_DCN = 1 };
+
+struct ProgParams {
+  int n_layers;
+  int SA, SB, a_stage_bytes, b_stage_bytes;   // one shared-memory carve-up for every layer
+  unsigned int* counter;                      // arrivals since the counter was zeroed
+  unsigned int base;                          // arrivals issued before this launch
+  int kind[PROG_MAX_LAYERS];
+  PPDcnArgs dcn[PROG_MAX_LAYERS];
+  HaloParams layer[PROG_MAX_LAYERS];
+};
+
+__device__ __forceinline__ void prog_wait(const unsigned int* counter, unsigned int target) {
+  unsigned int v, spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if ((int)(v - target) >= 0) return;
+    if ((++spins & 0xFFFu) == 0) {       // a lost arrival must not hang the GPU: trap after ~2 s
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_constant__ ProgParams P) {
+  using namespace ppx;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_b = smem + P.SA * P.a_stage_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + P.SB * P.b_stage_bytes);
+  uint64_t* a_empty = a_full + MAX_SA;
+  uint64_t* b_full = a_empty + MAX_SA;
+  uint64_t* b_empty = b_full + MAX_SB;
+  uint64_t* acc_full = b_empty + MAX_SB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2 + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned int G = gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < P.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < P.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], NUM_EPI_THREADS); }
+    mbar_fence_init();
+  }
+  if (warp == WARP_MMA) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue warps (+ the sampling layers)
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int r = quarter * 32 + lane;
+    int it = 0;
+    for (int li = 0; li < P.n_layers; ++li) {
+      if (li > 0) {        // inputs of this layer (residuals, sampling sources) were written by the previous one
+        if (lane == 0) prog_wait(P.counter, P.base + (unsigned int)li * G);
+        __syncwarp();
+      }
+      if (P.kind[li] == PROG_DCN) {
+        const PPDcnArgs& a = P.dcn[li];
+        const unsigned per_img = (unsigned)(a.H * a.W * 144);
+        const unsigned total = per_img * (unsigned)a.N;
+        for (unsigned idx = blockIdx.x * NUM_EPI_THREADS + tid; idx < total; idx += G * NUM_EPI_THREADS) {
+          const unsigned n = idx / per_img;
+          if (a.C == 128) dcn_sample_item<8, true>(a, idx - n * per_img, (int)n);
+          else dcn_sample_item<16, true>(a, idx - n * per_img, (int)n);
+        }
+      } else {
+        const HaloParams& h = P.layer[li];
+        const PPConvParams& p = h.c;
+        const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * p.groups;
+        const uint32_t set_cols = (uint32_t)(h.MT * h.accw);
+        const int epi = p.epi;
+        const bool vec = p.vec_ok != 0;
+        const bool has_aux = p.aux0 != nullptr;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += G, ++it) {
+          const TileCoord t = decode_tile(h, tile);
+          const int n0 = t.n_idx * p.BN;
+          const int bnt = min(p.BN, p.Cout_g_pad - n0);
+          const int set = it & 1;
+          int sub = 0, c_lo = 0, c_hi = bnt;
+          if (h.MT == 2) sub = half;
+          else {
+            const int split = ((bnt / 16 + 1) / 2) * 16;
+            c_lo = half ? split : 0;
+            c_hi = half ? bnt : split;
+          }
+          bool mvalid;
+          long long mrow;
+          if (h.flat) {
+            mrow = ((long long)t.tx * h.MT + sub) * 128 + r;
+            mvalid = mrow < p.M_total;
+          } else {
+            const int oy = t.ty * 16 + (r >> 3), ox = t.tx * (8 * h.MT) + 8 * sub + (r & 7);
+            mvalid = oy < p.OH && ox < p.OW;
+            mrow = ((long long)t.img * p.OH + oy) * p.OW + ox;
+          }
+          mbar_wait(&acc_full[set], (uint32_t)(it >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + lane_base + set * 256u + sub * h.accw;
+          (void)set_cols;
+          for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+            uint32_t raw0[16], raw1[16];
+            const bool two = c0 + 16 < c_hi;
+            tmem_ld16(t_row + c0, raw0);
+            if (two) tmem_ld16(t_row + c0 + 16, raw1);
+            const bool do0 = mvalid && n0 + c0 < p.Cout_g, do1 = mvalid && two && n0 + c0 + 16 < p.Cout_g;
+            ppconv::EpiAux x0, x1;
+            x0.have = x1.have = false;
+            if (has_aux) {
+              if (do0) ppconv::conv_epilogue_prefetch16(p, mrow, n0 + c0, epi, vec, x0);
+              if (do1) ppconv::conv_epilogue_prefetch16(p, mrow, n0 + c0 + 16, epi, vec, x1);
+            }
+            tmem_ld_wait();
+            if (c0 + 32 >= c_hi) {
+              tc_fence_before();
+              mbar_arrive(&acc_empty[set]);
+            }
+            if (do0) ppconv::conv_epilogue16(p, raw0, mrow, t.g, n0 + c0, epi, vec, &x0);
+            if (do1) ppconv::conv_epilogue16(p, raw1, mrow, t.g, n0 + c0 + 16, epi, vec, &x1);
+          }
+          if (c_lo >= c_hi) {
+            tc_fence_before();
+            mbar_arrive(&acc_empty[set]);
+          }
+        }
+      }
+      // publish this CTA's part of the layer: stores -> async proxy, CTA-wide meet of the writers, one arrival
+      fence_proxy_async_global();
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_THREADS) : "memory");
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(P.counter, 1u);
+      }
+    }
+  } else if (warp == WARP_A) {
+    // ------------------------------------------------------------------ input patch producer (TMA)
+    if (ppx::elect_one()) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int li = 0; li < P.n_layers; ++li) {
+        if (P.kind[li] != PROG_CONV) continue;
+        const HaloParams& h = P.layer[li];
+        const PPConvParams& p = h.c;
+        if (li > 0) {
+          prog_wait(P.counter, P.base + (unsigned int)li * G);
+          fence_proxy_async_global();
+        }
+        const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * p.groups;
+        const uint32_t bytes = (uint32_t)(h.BW * h.BH * 128);
+        for (int tile = blockIdx.x; tile < total_tiles; tile += G) {
+          const TileCoord t = decode_tile(h, tile);
+          const int x0 = h.flat ? t.tx * (128 * h.MT) : t.tx * (8 * h.MT) - p.pw, y0 = h.flat ? 0 : t.ty * 16 - p.ph;
+          for (int c = 0; c < h.chunks; ++c) {
+            const int ci = c * 64;
+            int q = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+              if (k < p.nseg && ci >= p.seg[k].cbegin) q = k;
+            const int ch0 = t.g * p.seg[q].gstep + (ci - p.seg[q].cbegin);
+            mbar_wait(&a_empty[s], phase ^ 1);
+            mbar_arrive_expect_tx(&a_full[s], bytes);
+            tma_load_4d(smem_u32(smem + s * P.a_stage_bytes), &h.tmap[q], ch0, x0, y0, t.img, &a_full[s]);
+            if (++s == P.SA) { s = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == WARP_B) {
+    // ------------------------------------------------------------------ weight tile producer: never waits for a layer
+    if (ppx::elect_one()) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int li = 0; li < P.n_layers; ++li) {
+        if (P.kind[li] != PROG_CONV) continue;
+        const HaloParams& h = P.layer[li];
+        const PPConvParams& p = h.c;
+        const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * p.groups;
+        const int taps = p.kh * p.kw;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += G) {
+          const TileCoord t = decode_tile(h, tile);
+          const int n0 = t.n_idx * p.BN;
+          const uint32_t bytes = (uint32_t)(min(p.BN, p.Cout_g_pad - n0) * 128);
+          const __half* wbase = p.wpacked + ((long long)t.g * p.num_kc * p.Cout_g_pad + n0) * 64;
+          for (int c = 0; c < h.chunks; ++c) {
+            for (int tap = 0; tap < taps; ++tap) {
+              const int kc = tap * h.chunks + c;
+              mbar_wait(&b_empty[s], phase ^ 1);
+              mbar_arrive_expect_tx(&b_full[s], bytes);
+              bulk_g2s(smem_u32(smem_b + s * P.b_stage_bytes), wbase + (long long)kc * p.Cout_g_pad * 64, bytes, &b_full[s]);
+              if (++s == P.SB) { s = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (ppx::elect_one()) {
+      int sa = 0, sb = 0, it = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint64_t b_hi = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint32_t a_base0 = (smem_u32(smem) & 0x3FFFF) >> 4, b_base0 = (smem_u32(smem_b) & 0x3FFFF) >> 4;
+      const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4, b_stage16 = (uint32_t)P.b_stage_bytes >> 4;
+      for (int li = 0; li < P.n_layers; ++li) {
+        if (P.kind[li] != PROG_CONV) continue;
+        const HaloParams& h = P.layer[li];
+        const PPConvParams& p = h.c;
+        const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * p.groups;
+        const int taps = p.kh * p.kw;
+        const uint32_t sbo = h.flat ? 1024u : (uint32_t)h.BW * 128;
+        const uint64_t a_hi = ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+        const uint32_t step_x = (uint32_t)p.dw * 8;
+        const uint32_t step_row = (uint32_t)(p.dh * h.BW - (p.kw - 1) * p.dw) * 8;
+        const uint32_t sub16 = (uint32_t)h.sub_bytes >> 4;
+        const bool two = h.MT == 2;
+        const int kw = p.kw;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += G, ++it) {
+          const int n0 = (tile % h.n_tiles) * p.BN;
+          const uint32_t idesc = umma_idesc_f16(128, (uint32_t)min(p.BN, p.Cout_g_pad - n0));
+          const int set = it & 1;
+          mbar_wait(&acc_empty[set], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + set * 256u, d1 = d0 + h.accw;
+          uint32_t accum = 0;
+          for (int c = 0; c < h.chunks; ++c) {
+            mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+            uint64_t adesc = a_hi | (uint64_t)(a_base0 + sa * a_stage16);
+            int kx = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint64_t bdesc = b_hi | (uint64_t)(b_base0 + sb * b_stage16);
+              umma_f16(d0, adesc, bdesc, idesc, accum);
+              umma_f16(d0, adesc + 2, bdesc + 2, idesc, 1u);
+              umma_f16(d0, adesc + 4, bdesc + 4, idesc, 1u);
+              umma_f16(d0, adesc + 6, bdesc + 6, idesc, 1u);
+              if (two) {
+                const uint64_t adesc1 = adesc + sub16;
+                umma_f16(d1, adesc1, bdesc, idesc, accum);
+                umma_f16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                umma_f16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                umma_f16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+              }
+              accum = 1u;
+              umma_commit(&b_empty[sb]);
+              if (++sb == P.SB) { sb = 0; pb ^= 1; }
+              adesc += step_x;
+              if (++kx == kw) { kx = 0; adesc += step_row - step_x; }
+            }
+            umma_commit(&a_empty[sa]);
+            if (++sa == P.SA) { sa = 0; pa ^= 1; }
+          }
+          umma_commit(&acc_full[set]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -431,10 +729,9 @@ int pp_conv_halo_eligible(const PPConvParams& p) {
   return encode_fn() != nullptr ? 1 : 0;
 }
 
-int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
-  HaloParams h;
-  h.c = pin;
-  PPConvParams& p = h.c;
+namespace {
+
+int halo_num_sms(int* out) {
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -442,7 +739,20 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
     PP_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     PP_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     PP_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    PP_CUDA_CHECK(cudaFuncSetAttribute(conv_prog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   }
+  *out = num_sms;
+  return PP_OK;
+}
+
+// Tile shape, pipeline depth and tensor maps of one layer.  one_wave: the layer is one of a multi-layer program whose
+// layers are separated by grid-wide barriers -- prefer a tile count just below the SM count (a second, partial wave
+// doubles the layer's latency) over fewer weight re-reads.
+int halo_configure(const PPConvParams& pin, HaloParams& h, bool one_wave) {
+  h.c = pin;
+  PPConvParams& p = h.c;
+  int num_sms = 0;
+  PP_TRY(halo_num_sms(&num_sms));
   const bool flat = p.kh * p.kw == 1;
   // N tile: <= 128 columns (two accumulator sets x two sub-tiles fill the 512 TMEM columns)
   const int n_tiles0 = pp_ceil_div(p.Cout_g_pad, 128);
@@ -456,6 +766,14 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
   int mt = 2;
   if (!p.ups2x && count(2, bn) < num_sms) mt = 1;
   while (count(mt, bn) < num_sms && bn >= 64 && bn % 32 == 0) bn /= 2;   // small launches: more, narrower tiles
+  if (one_wave && !p.ups2x) {
+    // largest tile count that still fits one wave: 128-pixel tiles, N split into 1..8 tiles of <= 256 columns
+    for (int nt = 8; nt >= 1; --nt) {
+      const int b = pp_ceil_div(pp_ceil_div(p.Cout_g_pad, nt), 16) * 16;
+      if (b > 256 || b < 16) continue;
+      if (count(1, b) <= num_sms) { mt = 1; bn = b; break; }
+    }
+  }
   p.BN = bn;
   h.MT = mt;
   h.flat = flat ? 1 : 0;
@@ -512,7 +830,22 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
     PP_REQUIRE(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled failed (%d) for segment %d (cstride=%d W=%d H=%d N=%d)",
                (int)r, i, s.cstride, p.W, p.H, p.N);
   }
-  const size_t smem = (size_t)sa * h.a_stage_bytes + (size_t)sb * h.b_stage_bytes + 1024 + 512 + 2 * (size_t)h.l_stage_bytes +
+  return PP_OK;
+}
+
+inline long long halo_total_tiles(const HaloParams& h) {
+  return (long long)h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * h.c.groups;
+}
+
+}  // namespace
+
+int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
+  HaloParams h;
+  PP_TRY(halo_configure(pin, h, false));
+  int num_sms = 0;
+  PP_TRY(halo_num_sms(&num_sms));
+  const long long total_tiles = halo_total_tiles(h);
+  const size_t smem = (size_t)h.SA * h.a_stage_bytes + (size_t)h.SB * h.b_stage_bytes + 1024 + 512 + 2 * (size_t)h.l_stage_bytes +
                       (h.ups ? 1024 : 0);
   const int grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
   cudaLaunchConfig_t cfg;
@@ -528,6 +861,103 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
   cfg.numAttrs = 1;
   if (h.ups) PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<true>, h));
   else PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_halo_kernel<false>, h));
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---- multi-layer programs ------------------------------------------------------------------------------------------
+namespace {
+thread_local PPProgRecorder* g_recorder = nullptr;
+}
+
+struct PPProgRecorder {
+  ProgParams prog;
+  double flops = 0.0;
+  int n_conv = 0;
+};
+
+bool pp_prog_recording() { return g_recorder != nullptr; }
+
+int pp_prog_begin() {
+  PP_REQUIRE(g_recorder == nullptr, "conv program: already recording");
+  g_recorder = new PPProgRecorder();
+  memset(&g_recorder->prog, 0, sizeof(ProgParams));
+  return PP_OK;
+}
+
+void pp_prog_abort() {
+  delete g_recorder;
+  g_recorder = nullptr;
+}
+
+int pp_prog_eligible(const PPConvParams& p) { return pp_conv_halo_eligible(p) && !p.ups2x; }
+
+int pp_prog_record_conv(const PPConvParams& p) {
+  PPProgRecorder* r = g_recorder;
+  PP_REQUIRE(r != nullptr, "conv program: not recording");
+  PP_REQUIRE(r->prog.n_layers < PROG_MAX_LAYERS, "conv program: more than %d layers", PROG_MAX_LAYERS);
+  PP_REQUIRE(pp_prog_eligible(p), "conv program: layer is not a stride-1 TMA halo-kernel convolution");
+  const int li = r->prog.n_layers;
+  PP_TRY(halo_configure(p, r->prog.layer[li], true));
+  r->prog.kind[li] = PROG_CONV;
+  r->prog.n_layers++;
+  r->n_conv++;
+  return PP_OK;
+}
+
+int pp_prog_record_dcn(const PPDcnArgs& a) {
+  PPProgRecorder* r = g_recorder;
+  PP_REQUIRE(r != nullptr, "conv program: not recording");
+  PP_REQUIRE(r->prog.n_layers < PROG_MAX_LAYERS, "conv program: more than %d layers", PROG_MAX_LAYERS);
+  const int li = r->prog.n_layers;
+  r->prog.kind[li] = PROG_DCN;
+  r->prog.dcn[li] = a;
+  r->prog.n_layers++;
+  return PP_OK;
+}
+
+// Launches the recorded layers as ONE kernel (grid = one CTA per SM); `counter` is a zero-initialised device word shared
+// by all programs of a stream, `*arrivals` the host-side count of arrivals issued so far on it.
+int pp_prog_end(unsigned int* counter, unsigned int* arrivals, cudaStream_t stream) {
+  PPProgRecorder* r = g_recorder;
+  PP_REQUIRE(r != nullptr, "conv program: not recording");
+  g_recorder = nullptr;
+  std::unique_ptr<PPProgRecorder> guard(r);
+  ProgParams& P = r->prog;
+  if (P.n_layers == 0) return PP_OK;
+  int num_sms = 0;
+  PP_TRY(halo_num_sms(&num_sms));
+  int a_max = 1024, b_max = 2048;
+  for (int i = 0; i < P.n_layers; ++i)
+    if (P.kind[i] == PROG_CONV) {
+      if (P.layer[i].a_stage_bytes > a_max) a_max = P.layer[i].a_stage_bytes;
+      if (P.layer[i].b_stage_bytes > b_max) b_max = P.layer[i].b_stage_bytes;
+    }
+  int sa = 3, sb = 0;
+  for (; sa >= 2; --sa) {
+    sb = (SMEM_BUDGET - sa * a_max) / b_max;
+    if (sb >= 3) break;
+  }
+  PP_REQUIRE(sa >= 2 && sb >= 3, "conv program: stages do not fit shared memory (A %d B, B %d B)", a_max, b_max);
+  if (sb > MAX_SB) sb = MAX_SB;
+  P.SA = sa; P.SB = sb; P.a_stage_bytes = a_max; P.b_stage_bytes = b_max;
+  P.counter = counter;
+  P.base = *arrivals;
+  const int grid = num_sms;
+  *arrivals += (unsigned int)(P.n_layers * grid);
+  const size_t smem = (size_t)sa * a_max + (size_t)sb * b_max + 1024 + 512;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_prog_kernel, P));
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

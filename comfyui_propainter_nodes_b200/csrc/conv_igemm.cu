@@ -273,6 +273,7 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
                   al32(p.out2, p.out2_cstride, p.out2_coff, 0) && (p.epi != PP_EPI_GRU_ZR || ((p.Cout_g >> 1) % 16 == 0)))
                      ? 1 : 0;
   }
+  if (pp_prog_recording()) return pp_prog_record_conv(p);
   if (pp_conv_halo_eligible(p)) return pp_launch_conv_halo(p, stream);
   PP_REQUIRE(!p.ups2x, "conv: fused x2 upsampling needs the TMA halo kernel (stride 1, one input segment, even H and W)");
   for (int i = 0; i < p.nseg; ++i)

@@ -60,3 +60,16 @@ int pp_launch_conv(const PPConvParams& p, cudaStream_t stream);
 // PP_CONV_HALO=0 in the environment disables it).  `p` must already carry num_kc / vec_ok.
 int pp_conv_halo_eligible(const PPConvParams& p);
 int pp_launch_conv_halo(const PPConvParams& p, cudaStream_t stream);
+
+// Multi-layer programs (conv_halo.cu): between pp_prog_begin() and pp_prog_end() every eligible convolution handed to
+// pp_launch_conv and every pp_k_dcn_sample call of this thread is RECORDED instead of launched; pp_prog_end launches
+// the recorded, mutually dependent layers as ONE persistent kernel with grid-wide barriers between them.
+struct PPDcnArgs;
+struct PPProgRecorder;
+bool pp_prog_recording();
+int pp_prog_begin();
+void pp_prog_abort();
+int pp_prog_eligible(const PPConvParams& p);
+int pp_prog_record_conv(const PPConvParams& p);
+int pp_prog_record_dcn(const PPDcnArgs& a);
+int pp_prog_end(unsigned int* counter, unsigned int* arrivals, cudaStream_t stream);

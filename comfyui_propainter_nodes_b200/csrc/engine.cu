@@ -111,8 +111,15 @@ int PPConvCall::run(cudaStream_t st) {
   PP_REQUIRE(p.out != nullptr, "conv: no output set");
   p.OH = (p.H + 2 * p.ph - p.dh * (p.kh - 1) - 1) / p.sh + 1;
   p.OW = (p.W + 2 * p.pw - p.dw * (p.kw - 1) - 1) / p.sw + 1;
-  eng->launches++;
   const double rows = (double)p.N * p.OH * p.OW;
+  if (pp_prog_recording()) {     // part of a multi-layer program: recorded now, launched by pp_prog_end
+    auto it = eng->convs.find(name);
+    const double m = (it != eng->convs.end() && it->second.macs_per_pixel > 0.0) ? it->second.macs_per_pixel
+                                                                                 : (double)p.Cout_g * p.groups * p.kh * p.kw * p.Cin;
+    eng->prog_flops += 2.0 * rows * m;
+    return pp_launch_conv(p, st);
+  }
+  eng->launches++;
   double macs = (double)p.Cout_g * p.groups * p.kh * p.kw * p.Cin;
   if (eng->profile) {
     auto it = eng->convs.find(name);

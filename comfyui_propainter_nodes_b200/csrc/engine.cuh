@@ -59,6 +59,10 @@ struct PPEngine {
   // multi-GPU (comm.cu): NCCL communicator (ncclComm_t, opaque here) of this engine's process group
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // multi-layer programs (conv_halo.cu): barrier counter word on the device + arrivals issued on it so far
+  unsigned int* prog_counter = nullptr;
+  unsigned int prog_arrivals = 0;
+  double prog_flops = 0.0;   // algorithmic flops of the layers recorded since pp_prog_begin (profiling)
   long long launches = 0;  // kernels launched by this engine (for bench accounting)
   // optional per-kernel timing (CUDA events on the launch stream), see pp_profile_* in capi.cu
   struct ProfRec {

@@ -76,5 +76,11 @@ int pp_k_quantize_frames(const float* img, uint8_t* u8, float* frames, int T, in
 int pp_k_prepare_masks(const float* mask, int Tm, int T, int H, int W, int iters_flow, int iters_dil, uint8_t* scratch,
                        float* flow_masks, float* masks_dilated, cudaStream_t st);
 int pp_k_u8_to_unit_float(const uint8_t* src, float* dst, long long n, cudaStream_t st);
+int pp_k_resize_bicubic_u8(const uint8_t* src, uint8_t* dst, uint8_t* tmp, int* coef, size_t coef_ints, int T, int H, int W,
+                           int C, int OH, int OW, cudaStream_t st);
+int pp_k_quantize_u8(const float* img, uint8_t* u8, long long n, cudaStream_t st);
+int pp_k_u8_to_frames(const uint8_t* u8, float* frames, int T, int H, int W, cudaStream_t st);
+int pp_k_dilate_masks_u8(const uint8_t* mask_u8, int Tm, int T, int H, int W, int iters_flow, int iters_dil,
+                         float* flow_masks, float* masks_dilated, cudaStream_t st);
 
 

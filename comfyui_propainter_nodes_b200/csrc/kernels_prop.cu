@@ -1,6 +1,8 @@
 // Flow-guided propagation kernels: fused image-propagation step, flow warps, fb-consistency,
 // modulated deformable sampling, flow-completion pack/combine, 1/4 downsampling.
 #include "kernels.cuh"
+#include "conv_igemm.cuh"
+#include "dcn_sample.cuh"
 
 namespace {
 
@@ -334,68 +336,11 @@ __global__ void rfc_combine(const __half* __restrict__ pred, int pred_cs, const 
 // group's C/16 contiguous channels with 16-byte loads.
 // ------------------------------------------------------------------------------------------------
 template <int CPG>  // channels per offset group: 8 or 16
-__global__ void dcn_sample(const __half* __restrict__ x0, int x0_cs, int x0_co, int C0,
-                           const __half* __restrict__ x1, int x1_cs, int x1_co,
-                           const __half* __restrict__ offs, int offs_cs, const __half* __restrict__ flow, int flow_cs,
-                           int flow_co, float max_mag, __half* __restrict__ cols, int C, int N, int H, int W) {
+__global__ void dcn_sample(const PPDcnArgs a) {
   // grid = (chunks of one image's H*W*144 (pixel, group, tap) items, images): 32-bit index math
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (unsigned)(H * W * 144)) return;
-  const int gk = idx % 144u;           // g*9 + k  (g-major like the offset channels)
-  const int pix = idx / 144u;
-  const int g = gk / 9, k = gk - g * 9;
-  const int x = pix % (unsigned)W, y = pix / (unsigned)W;
-  const int n = blockIdx.y;
-  const long long m = (long long)n * H * W + pix;
-  const __half* o = offs + m * offs_cs;
-  float dy = max_mag * tanhf(__half2float(o[2 * gk]));
-  float dx = max_mag * tanhf(__half2float(o[2 * gk + 1]));
-  if (flow != nullptr) {
-    dx += __half2float(flow[m * flow_cs + flow_co]);
-    dy += __half2float(flow[m * flow_cs + flow_co + 1]);
-  }
-  const float mod = 1.f / (1.f + __expf(-__half2float(o[288 + gk])));
-  const float py = (float)(y - 1 + k / 3) + dy, px = (float)(x - 1 + k % 3) + dx;
-  float acc[CPG];
-#pragma unroll
-  for (int i = 0; i < CPG; ++i) acc[i] = 0.f;
-  if (py > -1.f && py < (float)H && px > -1.f && px < (float)W) {
-    const float fy = floorf(py), fx = floorf(px);
-    const int y0 = (int)fy, xx0 = (int)fx;
-    const float ay = py - fy, ax = px - fx;
-    const int c = g * CPG;  // channel inside cat(x0, x1)
-    const __half* src;
-    int cs;
-    if (c < C0) { src = x0 + x0_co + c; cs = x0_cs; }
-    else { src = x1 + x1_co + (c - C0); cs = x1_cs; }
-    src += (long long)n * H * W * cs;
-#pragma unroll
-    for (int corner = 0; corner < 4; ++corner) {
-      const int yy = y0 + (corner >> 1), xx = xx0 + (corner & 1);
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
-      const uint4* vp = reinterpret_cast<const uint4*>(src + ((long long)yy * W + xx) * cs);
-#pragma unroll
-      for (int v = 0; v < CPG / 8; ++v) {
-        const uint4 q = vp[v];
-        const __half2* hq = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __half22float2(hq[e]);
-          acc[v * 8 + 2 * e] += w * f.x;
-          acc[v * 8 + 2 * e + 1] += w * f.y;
-        }
-      }
-    }
-  }
-  __half* d = cols + m * (long long)(9 * C) + k * C + g * CPG;
-#pragma unroll
-  for (int v = 0; v < CPG / 8; ++v) {
-    __align__(16) __half2 h[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(mod * acc[v * 8 + 2 * e], mod * acc[v * 8 + 2 * e + 1]);
-    reinterpret_cast<uint4*>(d)[v] = *reinterpret_cast<uint4*>(h);
-  }
+  if (idx >= (unsigned)(a.H * a.W * 144)) return;
+  dcn_sample_item<CPG, false>(a, idx, blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -585,12 +530,15 @@ int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half
   if ((long long)N * H * W == 0) return PP_OK;
   PP_REQUIRE(N <= 65535 && (long long)H * W * 144 < (1LL << 31), "dcn_sample: %d images of %dx%d exceed the grid limits", N, W, H);
   const dim3 grid(pp_ceil_div(H * W * 144, TPB), N);
-  if (C == 128)
-    dcn_sample<8><<<grid, TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow, flow_cs,
-                                        flow_co, max_mag, cols, C, N, H, W);
-  else
-    dcn_sample<16><<<grid, TPB, 0, st>>>(x0, x0_cs, x0_co, C0, x1, x1_cs, x1_co, offs, offs_cs, flow,
-                                         flow_cs, flow_co, max_mag, cols, C, N, H, W);
+  PPDcnArgs a;
+  a.x0 = x0; a.x0_cs = x0_cs; a.x0_co = x0_co; a.C0 = C0;
+  a.x1 = x1; a.x1_cs = x1_cs; a.x1_co = x1_co;
+  a.offs = offs; a.offs_cs = offs_cs;
+  a.flow = flow; a.flow_cs = flow_cs; a.flow_co = flow_co;
+  a.max_mag = max_mag; a.cols = cols; a.C = C; a.N = N; a.H = H; a.W = W;
+  if (pp_prog_recording()) return pp_prog_record_dcn(a);     // multi-layer program (conv_halo.cu): runs inside it
+  if (C == 128) dcn_sample<8><<<grid, TPB, 0, st>>>(a);
+  else dcn_sample<16><<<grid, TPB, 0, st>>>(a);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

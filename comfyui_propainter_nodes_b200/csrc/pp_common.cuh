@@ -100,10 +100,18 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    unsigned int v;
-    do {
+    unsigned int v, spins = 0;
+    uint64_t t0 = 0;
+    for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-    } while (v < target);
+      if (v >= target) break;
+      if ((++spins & 0xFFFu) == 0) {     // a CTA that never arrives must not hang the GPU: trap after ~2 s
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) __trap();
+      }
+    }
   }
   __syncthreads();
 }

@@ -6,6 +6,7 @@
 // Frame order in every buffer is time-major: image index n = t*D + d.  A time slice is then D contiguous
 // images (what the propagation convs need), and the (3,1,1) dilation-2 temporal convs of the P3D blocks
 // become 2-D convs with kernel (3,1) over an "image" of height Tn and width D*h*w.
+#include <stdlib.h>
 #include <string.h>
 
 #include "engine.cuh"
@@ -28,6 +29,11 @@ inline void shard(int n, int parts, int k, int& lo, int& hi) {   // contiguous n
   const int base = n / parts, rem = n % parts;
   lo = k * base + (k < rem ? k : rem);
   hi = lo + base + (k < rem ? 1 : 0);
+}
+
+inline bool rfc_use_programs() {
+  const char* s = getenv("PP_PROG");
+  return s == nullptr || atoi(s) != 0;
 }
 
 // Temporal reach of the encoder: four P3D blocks, each a (3,1,1) dilation-2 conv (t-2, t, t+2) => a frame's
@@ -132,10 +138,19 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
     PP_TRY(pp_alloc(e, &aligned, slice, "rfc aligned"));
     PP_TRY(pp_alloc(e, &bb, slice, "rfc backbone tmp"));
     PP_CUDA_CHECK(cudaMemsetAsync(zero, 0, slice * sizeof(__half), st));
+    // One propagation step = 8 dependent layers over D*P pixels (3,600-7,200 at 640x360): as separate launches each
+    // costs 15-30 us of mostly fixed overhead, so a step runs as ONE multi-layer program (conv_halo.cu: persistent CTAs,
+    // grid-wide barrier between layers).  PP_PROG=0 falls back to one launch per layer.
+    const bool prog = rfc_use_programs();
+    struct ProgGuard {      // an error path between begin and end must not leave the recorder armed
+      bool armed = false;
+      ~ProgGuard() { if (armed) pp_prog_abort(); }
+    } pg;
     for (int mod = 0; mod < 2; ++mod) {
       const std::string m = mod == 0 ? "rfc.fp.backward_" : "rfc.fp.forward_";
       __half* feats = mod == 0 ? fb : ff;
       for (int i = 0; i < Tn; ++i) {
+        if (prog) { PP_TRY(pp_prog_begin()); pg.armed = true; e.prog_flops = 0.0; }
         const int idx = mod == 0 ? Tn - 1 - i : i;
         const int prev = mod == 0 ? idx + 1 : idx - 1, prev2 = mod == 0 ? idx + 2 : idx - 2;
         const __half* cur = mid + (size_t)idx * slice;
@@ -152,12 +167,14 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
                      .act(PP_ACT_LRELU, 0.1f).run(st));
           PP_TRY(PPConvCall(e, m + ".offset.3", D, h8, w8).in(o1, 128, 0, 128).out(offs, 432, 0).run(st));
           // modulated deformable conv on cat(prop, n2): sample -> GEMM (K = 9*256)
-          {
+          if (prog) {
+            PP_TRY(pp_k_dcn_sample(p1, 128, 0, 128, n2, 128, 0, 128, offs, 432, nullptr, 0, 0, 5.0f, cols, D, h8, w8, st));
+          } else {
             const double px = (double)D * P;
             PPProfScope ps(e, "dcn_sample", px, 0.0, px * (256 * 2 + 432 * 2 + 2304 * 2), st);
             PP_TRY(pp_k_dcn_sample(p1, 128, 0, 128, n2, 128, 0, 128, offs, 432, nullptr, 0, 0, 5.0f, cols, D, h8, w8, st));
+            e.launches++;
           }
-          e.launches++;
           PP_TRY(PPConvCall(e, m + ".dcn", D, h8, w8).in(cols, 2304, 0, 2304).geom(1, 1, 0, 0).out(aligned, 128, 0)
                      .run(st));
           prop = aligned;
@@ -170,6 +187,12 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
         PP_TRY(b0.run(st));
         PP_TRY(PPConvCall(e, m + ".backbone.1", D, h8, w8).in(bb, 128, 0, 128).out(feats + (size_t)idx * slice, 128, 0)
                    .residual(prop, 128, 0).run(st));
+        if (prog) {
+          PPProfScope ps(e, "conv:rfc.fp.step_program", (double)D * P, e.prog_flops, 0.0, st);
+          pg.armed = false;
+          PP_TRY(pp_prog_end(e.prog_counter, &e.prog_arrivals, st));
+          e.launches++;
+        }
       }
     }
 

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "pp_gen_end": (_I, [_VP]),
     "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "pp_preprocess": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "pp_preprocess_resize": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "pp_postprocess": (_I, [_VP, _VP, _VP, _LL, _VP]),
     "pp_launch_count": (_LL, [_VP]),
     "pp_workspace_peak": (_SZ, [_VP]),
@@ -551,20 +552,27 @@ class Engine:
                                           _ptr(frame_ids_dev), _ptr(first_visit_dev), l_t, H, W, int(bool(half_math)),
                                           self._stream()))
 
-    def preprocess(self, image, mask, flow_mask_dilates: int, mask_dilates: int):
-        """Device version of convert_image_to_frames + prepare_frames_and_masks for the no-resize case.
-        image [T,H,W,3] float 0..1, mask [T or 1,H,W] float (host or device)
-        -> frames [1,T,3,H,W], flow_masks [1,T,1,H,W], masks_dilated [1,T,1,H,W] (float32), originals uint8 [T,H,W,3]."""
+    def preprocess(self, image, mask, flow_mask_dilates: int, mask_dilates: int, process_size=None):
+        """Device version of convert_image_to_frames + prepare_frames_and_masks (reference utils/image_utils.py:98-197).
+        image [T,H,W,3] float 0..1, mask [T or 1,H,W] float32 (host or device); ``process_size`` = (width, height) to
+        resize to (PIL's 8-bit bicubic resampler, reproduced bit for bit on the device), default: the input size.
+        -> frames [1,T,3,h,w], flow_masks [1,T,1,h,w], masks_dilated [1,T,1,h,w] (float32), originals uint8 [T,h,w,3]."""
         img = image.to(self.device, torch.float32, non_blocking=True).contiguous()
         msk = mask.to(self.device, torch.float32, non_blocking=True).contiguous()
         T, H, W, _ = img.shape
-        orig = torch.empty(T, H, W, 3, device=self.device, dtype=torch.uint8)
-        frames = torch.empty(T, 3, H, W, device=self.device, dtype=torch.float32)
-        fm = torch.empty(T, 1, H, W, device=self.device, dtype=torch.float32)
+        ow, oh = (W, H) if process_size is None else (int(process_size[0]), int(process_size[1]))
+        orig = torch.empty(T, oh, ow, 3, device=self.device, dtype=torch.uint8)
+        frames = torch.empty(T, 3, oh, ow, device=self.device, dtype=torch.float32)
+        fm = torch.empty(T, 1, oh, ow, device=self.device, dtype=torch.float32)
         md = torch.empty_like(fm)
-        self._check(self.lib.pp_preprocess(self.h, _ptr(img), _ptr(msk), msk.shape[0], T, H, W, int(flow_mask_dilates),
-                                           int(mask_dilates), _ptr(orig), _ptr(frames), _ptr(fm), _ptr(md),
-                                           self._stream()))
+        if (ow, oh) == (W, H):
+            self._check(self.lib.pp_preprocess(self.h, _ptr(img), _ptr(msk), msk.shape[0], T, H, W, int(flow_mask_dilates),
+                                               int(mask_dilates), _ptr(orig), _ptr(frames), _ptr(fm), _ptr(md),
+                                               self._stream()))
+        else:
+            self._check(self.lib.pp_preprocess_resize(self.h, _ptr(img), _ptr(msk), msk.shape[0], T, H, W, oh, ow,
+                                                      int(flow_mask_dilates), int(mask_dilates), _ptr(orig), _ptr(frames),
+                                                      _ptr(fm), _ptr(md), self._stream()))
         return frames.unsqueeze(0), fm.unsqueeze(0), md.unsqueeze(0), orig
 
     def postprocess(self, comp_u8: torch.Tensor) -> torch.Tensor:

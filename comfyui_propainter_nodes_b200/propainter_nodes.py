@@ -110,12 +110,14 @@ class ProPainterInpaint:
         cfg = ProPainterConfig(ref_stride, neighbor_length, subvideo_length, raft_iter, fp16, n, device,
                                icfg.process_size)
         models = initialize_models(cfg.device, cfg.fp16)
-        if tuple(icfg.process_size) == tuple(input_size) and mask.dtype == torch.float32:
-            # no resize: quantisation and mask dilation run on the device with the same integer semantics (float32
-            # masks only: the reference scales only those by 255, other dtypes go to PIL unscaled -- host path below)
-            ft, fm, md, orig = models.raft_model.engine.preprocess(image, mask, flow_mask_dilates, mask_dilates)
+        if mask.dtype == torch.float32:
+            # quantisation, PIL's 8-bit bicubic resize and the mask dilations run on the device with the reference's
+            # integer semantics, bit for bit (float32 masks only: the reference scales only those by 255, other dtypes
+            # go to PIL unscaled -- host path below)
+            eng = models.raft_model.engine
+            eng.reserve_for_clip(n, icfg.process_size[1], icfg.process_size[0])
+            ft, fm, md, orig = eng.preprocess(image, mask, flow_mask_dilates, mask_dilates, icfg.process_size)
         else:
-            # PIL bicubic resize on the host keeps the reference's resampling bit-identical
             ft, fm, md, originals = iu.prepare_frames_and_masks(iu.convert_image_to_frames(image), mask, icfg, device)
             orig = torch.from_numpy(np.stack(originals))
         return _run(models, ft, fm, md, orig, cfg)

@@ -117,6 +117,12 @@ PP_API int pp_composite(pp_handle h, const void* pred_f16, const float* masks_di
 PP_API int pp_preprocess(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
                          int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8, float* frames, float* flow_masks,
                          float* masks_dilated, void* stream);
+/* The same with a resize to the processing size out_w x out_h (reference utils/image_utils.py:98-103: PIL
+ * Image.resize, bicubic, on the 8-bit frames and on the 8-bit mask images) done on the device, bit-identical to
+ * Pillow's 8-bit resampler (two passes, 22-bit fixed-point coefficients).  Outputs have the processing size. */
+PP_API int pp_preprocess_resize(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
+                                int out_h, int out_w, int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8,
+                                float* frames, float* flow_masks, float* masks_dilated, void* stream);
 /* uint8 frames -> float32 / 255 (reference handle_output, utils/image_utils.py:276-290). */
 PP_API int pp_postprocess(pp_handle h, const uint8_t* comp_u8, float* image_out, long long n, void* stream);
 
