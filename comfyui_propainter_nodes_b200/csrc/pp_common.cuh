@@ -78,6 +78,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
 // wall clock instead of hanging the GPU; the host then sees cudaErrorLaunchFailure from the next CUDA call.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#ifdef PP_MBAR_UNBOUNDED   // A/B builds: the plain spin
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+  return;
+#endif
   if (mbar_try_wait(addr, parity)) return;
   uint32_t spins = 0;
   uint64_t t0 = 0;

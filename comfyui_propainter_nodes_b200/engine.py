@@ -17,7 +17,7 @@ from . import weights as Wspec
 
 _LIB = None
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libpropainter_b200.so")
+LIB_PATH = os.environ.get("PP_LIB_PATH") or os.path.join(_PKG_DIR, "libpropainter_b200.so")   # PP_LIB_PATH: A/B builds
 
 MAX_BN = 256
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_TANH, ACT_GELU = range(6)
@@ -474,21 +474,24 @@ class Engine:
         self._check(self.lib.pp_gen_window(self.h, ids, len(frame_ids), int(l_t), _ptr(pred), self._stream()))
         return pred
 
-    def gen_slot_bytes(self) -> int:
-        """Workspace one (window, frame) slot of pp_gen_run needs: window-major features, token / qkv / FFN rows of
-        the transformer, and its share of the feature-propagation and decoder buffers (generator.cu)."""
-        T, H, W = self._gen_shape
+    @staticmethod
+    def gen_slot_bytes(H: int, W: int) -> int:
+        """Workspace one (window, frame) slot of pp_gen_run needs (generator.cu): window-major features and the token /
+        qkv / FFN rows of the transformer (all slots alive together), plus an upper bound of the feature-propagation
+        buffers (4 feature-sized tensors per LOCAL slot of the largest equal-length group, and the per-step condition /
+        offset / sampled-column tensors, one set per window ~ 1/8 of a slot)."""
         p4 = (H // 4) * (W // 4)
         gh, gw = (H // 4 + 6 - 7) // 3 + 1, (W // 4 + 6 - 7) // 3 + 1
         rows_pad = -(-gh // 5) * 5 * (-(-gw // 9) * 9)
         xfmr = p4 * (256 + 80) + gh * gw * 2 * (512 * 3 + 1960) + rows_pad * 2 * (512 + 1536)
-        featprop = p4 * 2 * (128 * 5 + 264 + 432 + 1152 + 128 * 3)
+        featprop = p4 * 2 * (128 * 4) + p4 * 2 * (264 + 432 + 1152 + 128 * 3) // 8
         return int(1.25 * (xfmr + featprop))
 
-    def gen_batches(self, windows, budget_bytes: int):
+    def gen_batches(self, windows, budget_bytes: int, shape=None):
         """Split the schedule into consecutive sub-batches whose slots fit `budget_bytes` (windows are independent;
         the composite order is the window order, which consecutive sub-batches keep)."""
-        per_slot = self.gen_slot_bytes()
+        T, H, W = shape if shape is not None else self._gen_shape
+        per_slot = self.gen_slot_bytes(H, W)
         out, cur, used = [], [], 0
         for w in windows:
             need = (len(w[0]) + len(w[1])) * per_slot
@@ -511,7 +514,7 @@ class Engine:
         T, H, W = self._gen_shape
         enc_bytes = T * (H // 4) * (W // 4) * (256 + 32) + (64 << 20)          # the session's resident part
         decoder_reserve = 24 * H * W * 2 * 200                                   # room for a useful decoder chunk
-        budget = max(self.workspace.numel() - enc_bytes - decoder_reserve, self.gen_slot_bytes())
+        budget = max(self.workspace.numel() - enc_bytes - decoder_reserve, self.gen_slot_bytes(H, W))
         out = [self._gen_run_or_split(b) for b in self.gen_batches(list(windows), budget)]
         return out[0] if len(out) == 1 else torch.cat(out, 0)
 

@@ -80,6 +80,14 @@ def main():
             for it in cases.RAFT20_ITERS:
                 out[f"raft20_{tag}_it{it}_s4"] = preds[it - 1][:, :, ::4, ::4]   # every 4th pixel of flow_up
             out[f"raft20_{tag}_final_s2"] = preds[-1][:, :, ::2, ::2]
+            # sensitivity of the fp32 reference itself: the same network on input frames rounded to fp16 (a relative
+            # perturbation <= 4.9e-4, applied ONCE).  With random weights the 20-step recursion amplifies any
+            # perturbation; this is the yardstick the fp16 engine (which rounds at every layer) is measured against.
+            frh = fr.half().float()
+            pert = net(frh[0, :-1], frh[0, 1:], iters=max(cases.RAFT20_ITERS), test_mode=False)
+            sens = [[float((preds[it - 1] - pert[it - 1]).abs().mean()), float((preds[it - 1] - pert[it - 1]).abs().max())]
+                    for it in cases.RAFT20_ITERS]
+            out[f"raft20_{tag}_sens"] = torch.tensor(sens)       # [iteration][mean, max] in px
             print(f"raft20 {tag}: {time.time() - t0:.1f} s, |flow| mean {float(preds[-1].abs().mean()):.3f} "
                   f"max {float(preds[-1].abs().max()):.3f}", flush=True)
 
