@@ -419,6 +419,7 @@ __device__ __forceinline__ void prog_wait(const unsigned int* counter, unsigned 
   for (;;) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     if ((int)(v - target) >= 0) return;
+    __nanosleep(64);                      // one poller per CTA, backed off: the arrivals' atomics are not starved
     if ((++spins & 0xFFFu) == 0) {       // a lost arrival must not hang the GPU: trap after ~2 s
       uint64_t now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -441,11 +442,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
   uint64_t* b_empty = b_full + MAX_SB;
   uint64_t* acc_full = b_empty + MAX_SB;
   uint64_t* acc_empty = acc_full + 2;
+  uint64_t* layer_go = acc_empty + 2;     // the CTA's one poller (TMA producer thread) -> epilogue warps: layer li may start
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2 + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned int G = gridDim.x;
   if (tid == 0) {
+    mbar_init(layer_go, 1);
     for (int s = 0; s < P.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < P.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], NUM_EPI_THREADS); }
@@ -469,18 +472,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
     const int r = quarter * 32 + lane;
     int it = 0;
     for (int li = 0; li < P.n_layers; ++li) {
-      if (li > 0) {        // inputs of this layer (residuals, sampling sources) were written by the previous one
-        if (lane == 0) prog_wait(P.counter, P.base + (unsigned int)li * G);
-        __syncwarp();
-      }
+      // inputs of this layer (residuals, sampling sources) were written by the previous one: the producer thread polls
+      // the grid counter for the whole CTA and releases the epilogue warps through a shared-memory barrier
+      mbar_wait(layer_go, (uint32_t)li & 1u);
       if (P.kind[li] == PROG_DCN) {
         const PPDcnArgs& a = P.dcn[li];
         const unsigned per_img = (unsigned)(a.H * a.W * 144);
         const unsigned total = per_img * (unsigned)a.N;
-        for (unsigned idx = blockIdx.x * NUM_EPI_THREADS + tid; idx < total; idx += G * NUM_EPI_THREADS) {
-          const unsigned n = idx / per_img;
-          if (a.C == 128) dcn_sample_item<8, true>(a, idx - n * per_img, (int)n);
-          else dcn_sample_item<16, true>(a, idx - n * per_img, (int)n);
+        const unsigned stride = G * NUM_EPI_THREADS;
+        // 4 independent items per pass: their offset loads and corner gathers overlap (one item is a chain of two
+        // dependent L2 round trips, and there are only 256 sampling threads per SM here)
+        for (unsigned idx = blockIdx.x * NUM_EPI_THREADS + tid; idx < total; idx += 4 * stride) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const unsigned i2 = idx + u * stride;
+            if (i2 < total) {
+              const unsigned n = i2 / per_img;
+              if (a.C == 128) dcn_sample_item<8, true>(a, i2 - n * per_img, (int)n);
+              else dcn_sample_item<16, true>(a, i2 - n * per_img, (int)n);
+            }
+          }
         }
       } else {
         const HaloParams& h = P.layer[li];
@@ -556,13 +567,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
       int s = 0;
       uint32_t phase = 0;
       for (int li = 0; li < P.n_layers; ++li) {
-        if (P.kind[li] != PROG_CONV) continue;
-        const HaloParams& h = P.layer[li];
-        const PPConvParams& p = h.c;
-        if (li > 0) {
+        if (li > 0) {     // the CTA's only poller: every CTA finished layer li-1
           prog_wait(P.counter, P.base + (unsigned int)li * G);
           fence_proxy_async_global();
         }
+        mbar_arrive(layer_go);
+        if (P.kind[li] != PROG_CONV) continue;
+        const HaloParams& h = P.layer[li];
+        const PPConvParams& p = h.c;
         const int total_tiles = h.n_tiles * h.tiles_x * h.tiles_y * h.n_img * p.groups;
         const uint32_t bytes = (uint32_t)(h.BW * h.BH * 128);
         for (int tile = blockIdx.x; tile < total_tiles; tile += G) {

@@ -211,7 +211,7 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
   // one index table for every gather of this call
   std::vector<int> tab;
   auto push = [&](const std::vector<int>& v) { const int o = (int)tab.size(); tab.insert(tab.end(), v.begin(), v.end()); return o; };
-  struct Group { int L, n; std::vector<int> wins; int o_x, o_ff, o_scatter_src, o_scatter_dst; };
+  struct Group { int L, n; std::vector<int> wins; int o_x, o_ff, o_sc_src, o_sc_dst; };
   std::vector<Group> groups;
   for (int L : lts) {
     Group G; G.L = L;
@@ -221,6 +221,11 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
     for (int k = 0; k < L; ++k) for (int w : G.wins) ix.push_back(f0[w] + k);          // [k][w] <- session frame
     for (int k = 0; k < L - 1; ++k) for (int w : G.wins) ifl.push_back(f0[w] + k);     // [k][w] <- session flow
     G.o_x = push(ix); G.o_ff = push(ifl);
+    // scatter of the group's results [k][w] into the window-major slots
+    std::vector<int> sc_src, sc_dst;
+    for (int k = 0; k < L; ++k)
+      for (int j = 0; j < G.n; ++j) { sc_src.push_back(k * G.n + j); sc_dst.push_back(foff[G.wins[j]] + k); }
+    G.o_sc_src = push(sc_src); G.o_sc_dst = push(sc_dst);
     groups.push_back(G);
   }
   // refs: window-major slot <- session frame
@@ -230,9 +235,9 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
     for (int i = win_lt[w]; i < win_t[w]; ++i) { ref_dst.push_back(foff[w] + i); ref_src.push_back(frame_ids[foff[w] + i]); }
     for (int k = 0; k < win_lt[w]; ++k) loc_rows.push_back(foff[w] + k);                // local frame -> window-major slot
   }
+  const int o_ref_dst = push(ref_dst);
   const int o_ref_src = push(ref_src), o_loc = push(loc_rows), o_f0 = push(sw_f0), o_lt = push(sw_lt), o_t = push(sw_t),
             o_foff = push(sw_foff);
-  (void)ref_dst;
 
   const size_t mark0 = e.arena.mark();
   int* tab_dev;
@@ -313,18 +318,14 @@ int pp_stage_gen_run(PPEngine& e, const int* frame_ids, const int* win_t, const 
     PP_TRY(PPConvCall(e, "gen.fp.fuse.0", L * n, h4, w4).in(ob, 128, 0, 128).in(of, 128, 0, 128).in(M2, 8, 0, 8)
                .out(bb, 128, 0).act(PP_ACT_LRELU, 0.2f).run(st));
     PP_TRY(PPConvCall(e, "gen.fp.fuse.1", L * n, h4, w4).in(bb, 128, 0, 128).out(of, 128, 0).residual(X, 128, 0).run(st));
-    // scatter [k][w] -> window-major slots (async D2D copies: n*L small, frame sized)
-    for (int k = 0; k < L; ++k)
-      for (int j = 0; j < n; ++j)
-        PP_CUDA_CHECK(cudaMemcpyAsync(encw + (size_t)(foff[G.wins[j]] + k) * fsz, of + ((size_t)k * n + j) * fsz,
-                                      fsz * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    // scatter [k][w] -> window-major slots: one launch
+    PP_TRY(pp_k_copy_blocks(encw, tab_dev + G.o_sc_dst, of, tab_dev + G.o_sc_src, (long long)L * n, fsz * 2, st));
+    e.launches++;
     e.arena.release(mg);
   }
-  // reference frames straight from the encoder cache
-  for (size_t r = 0; r < ref_src.size(); ++r)
-    PP_CUDA_CHECK(cudaMemcpyAsync(encw + (size_t)ref_dst[r] * fsz, g.enc + (size_t)ref_src[r] * fsz, fsz * sizeof(__half),
-                                  cudaMemcpyDeviceToDevice, st));
-  (void)o_ref_src;
+  // reference frames straight from the encoder cache: one launch
+  PP_TRY(pp_k_copy_blocks(encw, tab_dev + o_ref_dst, g.enc, tab_dev + o_ref_src, (long long)ref_src.size(), fsz * 2, st));
+  e.launches++;
 
   // ---- SoftSplit: unfold(7,3,3) + Linear == 7x7 stride-3 conv (sparse_transformer.py:8-36) ------------
   const long long rows = (long long)TT * ng, rows_pad = (long long)TT * nh * nw;

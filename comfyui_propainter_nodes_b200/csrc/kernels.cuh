@@ -16,6 +16,8 @@ int pp_k_copy_channels(const __half* src, int src_cs, int src_co, __half* dst, i
 int pp_k_fill_f16(__half* dst, long long n, float v, cudaStream_t st);
 int pp_k_gather_blocks(void* dst, const void* src, const int* idx_dev, long long n, long long block_bytes,
                        cudaStream_t st);
+int pp_k_copy_blocks(void* dst, const int* dst_idx_dev, const void* src, const int* src_idx_dev, long long n,
+                     long long block_bytes, cudaStream_t st);
 
 // ---- RAFT (kernels_raft.cu) ---------------------------------------------------------------------
 int pp_k_instnorm_stats(const __half* x, int N, int HW, int C, float* sums /*[N][2][C]*/, cudaStream_t st);

@@ -117,6 +117,15 @@ __global__ void gather_blocks(uint4* __restrict__ dst, const uint4* __restrict__
   dst[i] = src[(long long)idx[j] * block16 + u];
 }
 
+// dst block dst_idx[j] <- src block src_idx[j] (scatter of per-window results into window-major slots)
+__global__ void copy_blocks(uint4* __restrict__ dst, const int* __restrict__ dst_idx, const uint4* __restrict__ src,
+                            const int* __restrict__ src_idx, long long n, long long block16) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n * block16) return;
+  const long long j = i / block16, u = i - j * block16;
+  dst[(long long)dst_idx[j] * block16 + u] = src[(long long)src_idx[j] * block16 + u];
+}
+
 __global__ void fill_f16(__half* dst, long long n, float v) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2half_rn(v);
@@ -172,6 +181,17 @@ int pp_k_gather_blocks(void* dst, const void* src, const int* idx_dev, long long
   const long long b16 = block_bytes / 16;
   gather_blocks<<<nblocks(n * b16), TPB, 0, st>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), idx_dev, n,
                                                    b16);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
+int pp_k_copy_blocks(void* dst, const int* dst_idx_dev, const void* src, const int* src_idx_dev, long long n,
+                     long long block_bytes, cudaStream_t st) {
+  PP_REQUIRE(block_bytes % 16 == 0, "copy_blocks: block size must be a multiple of 16 bytes");
+  if (n == 0) return PP_OK;
+  const long long b16 = block_bytes / 16;
+  copy_blocks<<<nblocks(n * b16), TPB, 0, st>>>(static_cast<uint4*>(dst), dst_idx_dev, static_cast<const uint4*>(src),
+                                                 src_idx_dev, n, b16);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

@@ -61,21 +61,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(addr), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline that never completes (bad tensor map, transaction-byte mismatch) traps after ~4 s of
-// wall clock instead of hanging the GPU; the host then sees cudaErrorLaunchFailure from the next CUDA call.
+// Bounded wait: a pipeline that never completes (bad tensor map, transaction-byte mismatch) traps instead of hanging
+// the GPU; the host then sees cudaErrorLaunchFailure from the next CUDA call.  The bound is an iteration count of the
+// (potentially blocking) try_wait -- 2^26 tries are >= 1 s even if every try returned at once -- so the retry path is
+// three extra integer instructions and the satisfied path is unchanged (a globaltimer-based bound cost 10 % on the
+// launch-latency-bound recurrent layers).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
 #ifdef PP_MBAR_UNBOUNDED   // A/B builds: the plain spin
@@ -90,19 +80,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(addr),
       "r"(parity)
       : "memory");
-  return;
+#else
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.lt.u32 p, n, 0x4000000;\n"
+      "@p bra WAIT_LOOP;\n"
+      "trap;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
 #endif
-  if (mbar_try_wait(addr, parity)) return;
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
-  while (!mbar_try_wait(addr, parity)) {
-    if ((++spins & 0x3FFFu) == 0) {
-      uint64_t now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();
-    }
-  }
 }
 
 // ------------------------------------------------------------------ grid-wide barrier (persistent kernels)

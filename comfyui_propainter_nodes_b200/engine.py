@@ -527,7 +527,10 @@ class Engine:
         half = len(windows) // 2                     # the estimate was too optimistic: halve and retry
         return torch.cat([self._gen_run_or_split(windows[:half]), self._gen_run_or_split(windows[half:])], 0)
 
+    gen_run_calls = 0       # engine passes issued by gen_run (1 per clip unless the workspace forced sub-batches)
+
     def _gen_run_once(self, windows) -> torch.Tensor:
+        self.gen_run_calls += 1
         T, H, W = self._gen_shape
         flat, wt, wl = [], [], []
         if getattr(self, "_gen_needed", None) is not None:

@@ -411,8 +411,8 @@ def check_small_workspace_fallback():
                                                          Wt.synthetic_generator_state_dict())
     ms = Models(StageHandle(small, "raft"), StageHandle(small, "flow"), StageHandle(small, "inpaint"))
     sched = PI.window_schedule(cfg)
-    n_batches = len(small.gen_batches(sched, small.workspace.numel(), (e["T"], e["H"], e["W"])))
     out = np.stack(PI.feature_propagation(ms.inpaint_model, uf, um, md, pf, orig, cfg))
+    n_batches = small.gen_run_calls            # engine passes the small arena forced for one clip
     # an impossible request fails loudly and leaves the arena as it was
     leaked = None
     try:
