@@ -408,6 +408,7 @@ struct ProgParams {
   int SA, SB, a_stage_bytes, b_stage_bytes;   // one shared-memory carve-up for every layer
   unsigned int* counter;                      // arrivals since the counter was zeroed
   unsigned int base;                          // arrivals issued before this launch
+  unsigned long long* ts;                     // debug (PP_PROG_TS=1): globaltimer of CTA 0 at [layer start, layer end]
   int kind[PROG_MAX_LAYERS];
   PPDcnArgs dcn[PROG_MAX_LAYERS];
   HaloParams layer[PROG_MAX_LAYERS];
@@ -475,6 +476,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
       // inputs of this layer (residuals, sampling sources) were written by the previous one: the producer thread polls
       // the grid counter for the whole CTA and releases the epilogue warps through a shared-memory barrier
       mbar_wait(layer_go, (uint32_t)li & 1u);
+      if (P.ts != nullptr && blockIdx.x == 0 && tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        P.ts[2 * li] = now;
+      }
       if (P.kind[li] == PROG_DCN) {
         const PPDcnArgs& a = P.dcn[li];
         const unsigned per_img = (unsigned)(a.H * a.W * 144);
@@ -559,6 +565,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
       if (tid == 0) {
         __threadfence();
         atomicAdd(P.counter, 1u);
+        if (P.ts != nullptr && blockIdx.x == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          P.ts[2 * li + 1] = now;
+        }
       }
     }
   } else if (warp == WARP_A) {
@@ -780,9 +791,11 @@ int halo_configure(const PPConvParams& pin, HaloParams& h, bool one_wave) {
   while (count(mt, bn) < num_sms && bn >= 64 && bn % 32 == 0) bn /= 2;   // small launches: more, narrower tiles
   if (one_wave && !p.ups2x) {
     // largest tile count that still fits one wave: 128-pixel tiles, N split into 1..8 tiles of <= 256 columns
+    static int min_bn = -1;
+    if (min_bn < 0) { const char* e = getenv("PP_PROG_MIN_BN"); min_bn = e != nullptr ? atoi(e) : 16; }
     for (int nt = 8; nt >= 1; --nt) {
       const int b = pp_ceil_div(pp_ceil_div(p.Cout_g_pad, nt), 16) * 16;
-      if (b > 256 || b < 16) continue;
+      if (b > 256 || b < 16 || (b < min_bn && nt > 1)) continue;
       if (count(1, b) <= num_sms) { mt = 1; bn = b; break; }
     }
   }
@@ -955,6 +968,14 @@ int pp_prog_end(unsigned int* counter, unsigned int* arrivals, cudaStream_t stre
   P.SA = sa; P.SB = sb; P.a_stage_bytes = a_max; P.b_stage_bytes = b_max;
   P.counter = counter;
   P.base = *arrivals;
+  static int ts_mode = -1, ts_printed = 0;
+  static unsigned long long* ts_dev = nullptr;
+  if (ts_mode < 0) {
+    const char* e = getenv("PP_PROG_TS");
+    ts_mode = (e != nullptr && atoi(e) != 0) ? atoi(e) : 0;
+    if (ts_mode) PP_CUDA_CHECK(cudaMalloc(&ts_dev, 2 * PROG_MAX_LAYERS * sizeof(unsigned long long)));
+  }
+  P.ts = (ts_mode && ts_printed < ts_mode) ? ts_dev : nullptr;
   const int grid = num_sms;
   *arrivals += (unsigned int)(P.n_layers * grid);
   const size_t smem = (size_t)sa * a_max + (size_t)sb * b_max + 1024 + 512;
@@ -971,5 +992,21 @@ int pp_prog_end(unsigned int* counter, unsigned int* arrivals, cudaStream_t stre
   cfg.numAttrs = 1;
   PP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_prog_kernel, P));
   PP_CUDA_CHECK(cudaGetLastError());
+  if (P.ts != nullptr) {      // debug: per-layer wall time of CTA 0 (serialises the stream)
+    unsigned long long h[2 * PROG_MAX_LAYERS];
+    PP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    PP_CUDA_CHECK(cudaMemcpy(h, ts_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    ++ts_printed;
+    fprintf(stderr, "[prog %d] %d layers:", ts_printed, P.n_layers);
+    for (int i = 0; i < P.n_layers; ++i) {
+      const HaloParams& L = P.layer[i];
+      if (P.kind[i] == PROG_CONV)
+        fprintf(stderr, " | conv K=%d N=%d bn=%d mt=%d tiles=%lld: %.1f us (gap %.1f)", L.c.K_total, L.c.Cout_g, L.c.BN, L.MT,
+                halo_total_tiles(L), (h[2 * i + 1] - h[2 * i]) / 1e3, i ? (h[2 * i] - h[2 * i - 1]) / 1e3 : 0.0);
+      else
+        fprintf(stderr, " | dcn: %.1f us (gap %.1f)", (h[2 * i + 1] - h[2 * i]) / 1e3, i ? (h[2 * i] - h[2 * i - 1]) / 1e3 : 0.0);
+    }
+    fprintf(stderr, " | total %.1f us\n", (h[2 * P.n_layers - 1] - h[0]) / 1e3);
+  }
   return PP_OK;
 }

@@ -1,5 +1,7 @@
 // Flow-guided propagation kernels: fused image-propagation step, flow warps, fb-consistency,
 // modulated deformable sampling, flow-completion pack/combine, 1/4 downsampling.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "conv_igemm.cuh"
 #include "dcn_sample.cuh"
@@ -537,6 +539,15 @@ int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half
   a.flow = flow; a.flow_cs = flow_cs; a.flow_co = flow_co;
   a.max_mag = max_mag; a.cols = cols; a.C = C; a.N = N; a.H = H; a.W = W;
   if (pp_prog_recording()) return pp_prog_record_dcn(a);     // multi-layer program (conv_halo.cu): runs inside it
+  {
+    // default: source tiles staged in shared memory by TMA (dcn_tiled.cu); PP_DCN_TILED=0 keeps the plain L2 sampler
+    const char* s = getenv("PP_DCN_TILED");       // read per call: tests compare both samplers in one process
+    if (s == nullptr || atoi(s) != 0) {
+      int handled = 0;
+      PP_TRY(pp_k_dcn_sample_tiled(a, 3, st, &handled));
+      if (handled) return PP_OK;
+    }
+  }
   if (C == 128) dcn_sample<8><<<grid, TPB, 0, st>>>(a);
   else dcn_sample<16><<<grid, TPB, 0, st>>>(a);
   PP_CUDA_CHECK(cudaGetLastError());

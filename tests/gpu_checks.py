@@ -396,6 +396,44 @@ def check_composite_exact():
     return res
 
 
+def check_step_variants():
+    """The recurrent propagation steps have three execution variants -- multi-layer program kernel (default), one launch
+    per layer with the TMA-staged deformable sampler, one launch per layer with the plain L2 sampler -- that perform the
+    same arithmetic in the same order: outputs must be bit-identical (flow completion, generator window)."""
+    import os
+    m = full_models()
+    eng = m.flow_model.engine
+    (ff, fb), masks = cases.rfc_case()
+    c = cases.window_case()
+    t, l_t = c["frames"].shape[1], c["l_t"]
+    H, W = c["frames"].shape[-2:]
+    wf = torch.zeros(t - 1, 2, H, W)
+    wb = torch.zeros(t - 1, 2, H, W)
+    wf[:l_t - 1], wb[:l_t - 1] = c["flows"][0][0], c["flows"][1][0]
+    outs = {}
+    keep = {k: os.environ.get(k) for k in ("PP_PROG", "PP_DCN_TILED")}
+    try:
+        for tag, env in (("program", {"PP_PROG": "1", "PP_DCN_TILED": "1"}), ("tiled", {"PP_PROG": "0", "PP_DCN_TILED": "1"}),
+                         ("plain", {"PP_PROG": "0", "PP_DCN_TILED": "0"})):
+            os.environ.update(env)
+            of, ob = eng.flow_complete(ff[0].to(DEV), fb[0].to(DEV), masks[0].to(DEV))
+            eng.gen_begin(c["frames"][0].to(DEV), c["masks_in"][0].to(DEV), c["masks_upd"][0].to(DEV), wf.to(DEV), wb.to(DEV))
+            pred = eng.gen_window(list(range(t)), l_t)
+            eng.gen_end()
+            torch.cuda.synchronize()
+            outs[tag] = (of.clone(), ob.clone(), pred.clone())
+    finally:
+        for k, v in keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    res = {}
+    for tag in ("program", "tiled"):
+        res[tag + "_vs_plain"] = [int((a != b).sum()) for a, b in zip(outs[tag], outs["plain"])]
+    return res
+
+
 def check_small_workspace_fallback():
     """A workspace far below what one batched pass needs: gen_run splits the schedule into sub-batches (down to one
     window) and the result is bit-identical; a failing call leaves the arena untouched (no leak)."""
@@ -438,7 +476,7 @@ def main():
                ("e2e", lambda: check_e2e(golden)), ("c1_node", lambda: check_c1_node(golden2)),
                ("raft20", lambda: check_raft20(golden2)), ("chunked", lambda: check_chunked(golden2)),
                ("outpaint_node", lambda: check_outpaint_node(golden2)), ("composite_exact", check_composite_exact),
-               ("small_workspace", check_small_workspace_fallback)]
+               ("small_workspace", check_small_workspace_fallback), ("step_variants", check_step_variants)]
     for name, fn in checks:
         if only and not any(o in name for o in only):
             continue
