@@ -5,10 +5,9 @@
 // sector bandwidth (ncu: long scoreboard 68 %, 1.4 TB/s algorithmic).  But the learned offsets are bounded
 // (max_mag * tanh, recurrent_flow_completion.py:40, propainter.py:66) so every sample of a TH x TW tile of output
 // pixels lies inside the tile grown by R = ceil(max_mag) + 2 pixels (+ a margin for the added flow in the feature
-// path).  Here one CTA owns a tile: per offset group it TMA-loads that box of the group's C/16 channels once
-// ([BH][BW][CPG] fp16, zero-filled outside the image = the sampler's zero padding), double-buffered over the 16
-// groups, and all (pixel, tap) items sample from shared memory.  L2 traffic per output pixel drops from 18 KB to
-// (BH*BW / (TH*TW)) * 2C bytes (1.8-3.9 KB).  A sample whose corners leave the staged box (possible only through a
+// path).  Here one CTA owns (tile, quad of 4 offset groups): ONE TMA box load lands [BH][BW][4*C/16] fp16 in shared
+// memory (zero-filled outside the image = the sampler's zero padding) and all (pixel, group, tap) items of the quad
+// sample from it.  L2 traffic per output pixel drops from 18 KB to (BH*BW / (TH*TW)) * 2C bytes (1.8-3.9 KB).  A sample whose corners leave the staged box (possible only through a
 // large flow in the feature path) falls back to global loads, so the result never depends on R.
 #include <cuda.h>
 
@@ -34,119 +33,115 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
       : "memory");
 }
 
+// One CTA = (tile, quad of 4 offset groups, image): ONE TMA box load of the quad's 4*CPG channels, then all 256
+// threads work through the tile's (pixel, group-in-quad, tap) items from shared memory.  No in-CTA pipeline: latency is
+// hidden by 3-4 resident CTAs per SM and 4x more CTAs than tiles.
 template <int CPG>
 __global__ void __launch_bounds__(NT) dcn_sample_tiled(const __grid_constant__ TiledParams P) {
   using namespace ppx;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);     // [2]
-  uint8_t* stage0 = smem + 128;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint8_t* box = smem + 128;
   const PPDcnArgs& a = P.a;
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x, n = blockIdx.y;
+  const int tile = blockIdx.x >> 2, quad = blockIdx.x & 3, n = blockIdx.y;
   const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
   const int y0 = ty * P.TH, x0 = tx * P.TW;              // tile origin
   const int by0 = y0 - P.R, bx0 = x0 - P.R;              // box origin (may be negative: zero-filled)
   const int H = a.H, W = a.W, C = a.C;
-  const uint32_t bytes = (uint32_t)(P.BH * P.BW * CPG * 2);
+  constexpr int QC = 4 * CPG;                            // channels of a quad
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    mbar_init(full, 1);
     mbar_fence_init();
+    const int c = quad * QC;                              // first channel inside cat(x0, x1)
+    const int q = c < a.C0 ? 0 : 1;
+    mbar_arrive_expect_tx(full, (uint32_t)(P.BH * P.BW * QC * 2));
+    tma_load_4d(smem_u32(box), &P.tmap[q], q ? c - a.C0 : c, bx0, by0, n, full);
   }
   __syncthreads();
-  auto issue = [&](int g, int s) {
-    const int c = g * CPG;                                // channel inside cat(x0, x1)
-    const int q = c < a.C0 ? 0 : 1;
-    mbar_arrive_expect_tx(&full[s], bytes);
-    tma_load_4d(smem_u32(stage0 + s * P.stage_bytes), &P.tmap[q], q ? c - a.C0 : c, bx0, by0, n, &full[s]);
-  };
-  if (tid == 0) issue(0, 0);
-  const int items = P.TH * P.TW * 9;
+  mbar_wait(full, 0);
+  const int items = P.TH * P.TW * 36;                    // (pixel, group in quad, tap)
   const long long img_px = (long long)n * H * W;
-  for (int g = 0; g < 16; ++g) {
-    const int s = g & 1;
-    if (tid == 0 && g + 1 < 16) issue(g + 1, s ^ 1);      // stage s^1 was released by the __syncthreads below
-    mbar_wait(&full[s], (uint32_t)(g >> 1) & 1u);
-    const uint8_t* box = stage0 + s * P.stage_bytes;
-    for (int it = tid; it < items; it += NT) {
-      const int k = it % 9, pp = it / 9;
-      const int py_i = pp / P.TW, px_i = pp - py_i * P.TW;
-      const int y = y0 + py_i, x = x0 + px_i;
-      if (y >= H || x >= W) continue;
-      const long long m = img_px + (long long)y * W + x;
-      const __half* o = a.offs + m * a.offs_cs;
-      const int gk = g * 9 + k;
-      float dy = a.max_mag * tanhf(__half2float(o[2 * gk]));
-      float dx = a.max_mag * tanhf(__half2float(o[2 * gk + 1]));
-      if (a.flow != nullptr) {
-        dx += __half2float(a.flow[m * a.flow_cs + a.flow_co]);
-        dy += __half2float(a.flow[m * a.flow_cs + a.flow_co + 1]);
-      }
-      const float mod = 1.f / (1.f + __expf(-__half2float(o[288 + gk])));
-      const float py = (float)(y - 1 + k / 3) + dy, px = (float)(x - 1 + k % 3) + dx;
-      float acc[CPG];
+  for (int it = tid; it < items; it += NT) {
+    const int gk4 = it % 36, pp = it / 36;
+    const int gq = gk4 / 9, k = gk4 - gq * 9;
+    const int g = quad * 4 + gq;
+    const int py_i = pp / P.TW, px_i = pp - py_i * P.TW;
+    const int y = y0 + py_i, x = x0 + px_i;
+    if (y >= H || x >= W) continue;
+    const long long m = img_px + (long long)y * W + x;
+    const __half* o = a.offs + m * a.offs_cs;
+    const int gk = g * 9 + k;
+    float dy = a.max_mag * tanhf(__half2float(o[2 * gk]));
+    float dx = a.max_mag * tanhf(__half2float(o[2 * gk + 1]));
+    if (a.flow != nullptr) {
+      dx += __half2float(a.flow[m * a.flow_cs + a.flow_co]);
+      dy += __half2float(a.flow[m * a.flow_cs + a.flow_co + 1]);
+    }
+    const float mod = 1.f / (1.f + __expf(-__half2float(o[288 + gk])));
+    const float py = (float)(y - 1 + k / 3) + dy, px = (float)(x - 1 + k % 3) + dx;
+    float acc[CPG];
 #pragma unroll
-      for (int i = 0; i < CPG; ++i) acc[i] = 0.f;
-      if (py > -1.f && py < (float)H && px > -1.f && px < (float)W) {
-        const float fy = floorf(py), fx = floorf(px);
-        const int yy0 = (int)fy, xx0 = (int)fx;
-        const float ay = py - fy, ax = px - fx;
-        const int ry = yy0 - by0, rx = xx0 - bx0;          // corner (0,0) inside the box?
-        if (ry >= 0 && rx >= 0 && ry + 1 < P.BH && rx + 1 < P.BW) {
+    for (int i = 0; i < CPG; ++i) acc[i] = 0.f;
+    if (py > -1.f && py < (float)H && px > -1.f && px < (float)W) {
+      const float fy = floorf(py), fx = floorf(px);
+      const int yy0 = (int)fy, xx0 = (int)fx;
+      const float ay = py - fy, ax = px - fx;
+      const int ry = yy0 - by0, rx = xx0 - bx0;          // corner (0,0) inside the box?
+      if (ry >= 0 && rx >= 0 && ry + 1 < P.BH && rx + 1 < P.BW) {
 #pragma unroll
-          for (int corner = 0; corner < 4; ++corner) {
-            const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
-            const uint4* vp = reinterpret_cast<const uint4*>(box + ((ry + (corner >> 1)) * P.BW + rx + (corner & 1)) * (CPG * 2));
+        for (int corner = 0; corner < 4; ++corner) {
+          const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
+          const uint4* vp = reinterpret_cast<const uint4*>(box + ((ry + (corner >> 1)) * P.BW + rx + (corner & 1)) * (QC * 2) +
+                                                            gq * (CPG * 2));
 #pragma unroll
-            for (int v = 0; v < CPG / 8; ++v) {
-              const uint4 qv = vp[v];
-              const __half2* hq = reinterpret_cast<const __half2*>(&qv);
+          for (int v = 0; v < CPG / 8; ++v) {
+            const uint4 qv = vp[v];
+            const __half2* hq = reinterpret_cast<const __half2*>(&qv);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(hq[e]);
-                acc[v * 8 + 2 * e] += w * f.x;
-                acc[v * 8 + 2 * e + 1] += w * f.y;
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(hq[e]);
+              acc[v * 8 + 2 * e] += w * f.x;
+              acc[v * 8 + 2 * e + 1] += w * f.y;
             }
           }
-        } else {
-          // outside the staged box (large flow): same arithmetic from global memory
-          const int c = g * CPG;
-          const __half* src;
-          int cs;
-          if (c < a.C0) { src = a.x0 + a.x0_co + c; cs = a.x0_cs; }
-          else { src = a.x1 + a.x1_co + (c - a.C0); cs = a.x1_cs; }
-          src += img_px * cs;
+        }
+      } else {
+        // outside the staged box (large flow): same arithmetic from global memory
+        const int c = g * CPG;
+        const __half* src;
+        int cs;
+        if (c < a.C0) { src = a.x0 + a.x0_co + c; cs = a.x0_cs; }
+        else { src = a.x1 + a.x1_co + (c - a.C0); cs = a.x1_cs; }
+        src += img_px * cs;
 #pragma unroll
-          for (int corner = 0; corner < 4; ++corner) {
-            const int yy = yy0 + (corner >> 1), xx = xx0 + (corner & 1);
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
-            const uint4* vp = reinterpret_cast<const uint4*>(src + ((long long)yy * W + xx) * cs);
+        for (int corner = 0; corner < 4; ++corner) {
+          const int yy = yy0 + (corner >> 1), xx = xx0 + (corner & 1);
+          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+          const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
+          const uint4* vp = reinterpret_cast<const uint4*>(src + ((long long)yy * W + xx) * cs);
 #pragma unroll
-            for (int v = 0; v < CPG / 8; ++v) {
-              const uint4 qv = vp[v];
-              const __half2* hq = reinterpret_cast<const __half2*>(&qv);
+          for (int v = 0; v < CPG / 8; ++v) {
+            const uint4 qv = vp[v];
+            const __half2* hq = reinterpret_cast<const __half2*>(&qv);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(hq[e]);
-                acc[v * 8 + 2 * e] += w * f.x;
-                acc[v * 8 + 2 * e + 1] += w * f.y;
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(hq[e]);
+              acc[v * 8 + 2 * e] += w * f.x;
+              acc[v * 8 + 2 * e + 1] += w * f.y;
             }
           }
         }
       }
-      __half* d = a.cols + m * (long long)(9 * C) + k * C + g * CPG;
-#pragma unroll
-      for (int v = 0; v < CPG / 8; ++v) {
-        __align__(16) __half2 h[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(mod * acc[v * 8 + 2 * e], mod * acc[v * 8 + 2 * e + 1]);
-        reinterpret_cast<uint4*>(d)[v] = *reinterpret_cast<uint4*>(h);
-      }
     }
-    __syncthreads();      // everyone is done with stage s before it is refilled (group g+2)
+    __half* d = a.cols + m * (long long)(9 * C) + k * C + g * CPG;
+#pragma unroll
+    for (int v = 0; v < CPG / 8; ++v) {
+      __align__(16) __half2 h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(mod * acc[v * 8 + 2 * e], mod * acc[v * 8 + 2 * e + 1]);
+      reinterpret_cast<uint4*>(d)[v] = *reinterpret_cast<uint4*>(h);
+    }
   }
 }
 
@@ -175,20 +170,21 @@ int pp_k_dcn_sample_tiled(const PPDcnArgs& a, int flow_margin, cudaStream_t st, 
   EncodeTiledFn enc = encode_fn();
   if (enc == nullptr) return PP_OK;
   const int cpg = a.C / 16;
-  if ((cpg != 8 && cpg != 16) || a.C0 % cpg != 0) return PP_OK;
+  if ((cpg != 8 && cpg != 16) || a.C0 % (4 * cpg) != 0) return PP_OK;   // a quad of groups never straddles x0 | x1
   if ((a.x0_cs % 8) || (a.x0_co % 8) || (a.x1 != nullptr && ((a.x1_cs % 8) || (a.x1_co % 8)))) return PP_OK;
   TiledParams P;
   P.a = a;
   const long long px = (long long)a.N * a.H * a.W;
-  // small problems (one wave of 16x16 tiles would leave most SMs idle): 8x8 tiles
-  const bool small = (long long)pp_ceil_div(a.H, 16) * pp_ceil_div(a.W, 16) * a.N < 148;
-  P.TH = P.TW = small ? 8 : 16;
   P.R = (int)ceilf(a.max_mag) + 2 + (a.flow != nullptr ? flow_margin : 0);
+  // 16x16 tiles when their box fits 96 KB and there are at least two waves of CTAs, else 8x8
+  const bool big = (size_t)(16 + 2 * P.R) * (16 + 2 * P.R) * 4 * cpg * 2 + 256 <= 96 * 1024 &&
+                   (long long)pp_ceil_div(a.H, 16) * pp_ceil_div(a.W, 16) * a.N * 4 >= 2 * 148;
+  P.TH = P.TW = big ? 16 : 8;
   P.BH = P.TH + 2 * P.R;
   P.BW = P.TW + 2 * P.R;
   P.tiles_x = pp_ceil_div(a.W, P.TW);
   P.tiles_y = pp_ceil_div(a.H, P.TH);
-  P.stage_bytes = pp_ceil_div(P.BH * P.BW * cpg * 2, 128) * 128;
+  P.stage_bytes = pp_ceil_div(P.BH * P.BW * 4 * cpg * 2, 128) * 128;
   if (P.BH > 256 || P.BW > 256 || a.N > 65535 || px == 0) return PP_OK;
   const __half* base[2] = {a.x0 + a.x0_co, a.x1 != nullptr ? a.x1 + a.x1_co : nullptr};
   const int cs[2] = {a.x0_cs, a.x1_cs}, cn[2] = {a.C0, a.C - a.C0};
@@ -197,14 +193,14 @@ int pp_k_dcn_sample_tiled(const PPDcnArgs& a, int flow_margin, cudaStream_t st, 
     if ((reinterpret_cast<uintptr_t>(base[q]) & 15) != 0) return PP_OK;
     cuuint64_t dims[4] = {(cuuint64_t)cn[q], (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.N};
     cuuint64_t strides[3] = {(cuuint64_t)cs[q] * 2, (cuuint64_t)a.W * cs[q] * 2, (cuuint64_t)a.H * a.W * cs[q] * 2};
-    cuuint32_t box[4] = {(cuuint32_t)cpg, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(4 * cpg), (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     const CUresult r = enc(&P.tmap[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base[q]), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PP_REQUIRE(r == CUDA_SUCCESS, "dcn_sample_tiled: cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
-  const size_t smem = 128 + 2 * (size_t)P.stage_bytes;
+  const size_t smem = 128 + (size_t)P.stage_bytes;
   static bool attr = false;
   if (!attr) {
     PP_CUDA_CHECK(cudaFuncSetAttribute(dcn_sample_tiled<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -212,7 +208,7 @@ int pp_k_dcn_sample_tiled(const PPDcnArgs& a, int flow_margin, cudaStream_t st, 
     attr = true;
   }
   if (smem > 96 * 1024) return PP_OK;
-  const dim3 grid(P.tiles_x * P.tiles_y, a.N);
+  const dim3 grid(P.tiles_x * P.tiles_y * 4, a.N);
   if (cpg == 8) dcn_sample_tiled<8><<<grid, NT, smem, st>>>(P);
   else dcn_sample_tiled<16><<<grid, NT, smem, st>>>(P);
   PP_CUDA_CHECK(cudaGetLastError());

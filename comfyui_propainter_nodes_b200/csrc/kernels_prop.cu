@@ -531,7 +531,6 @@ int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half
   PP_REQUIRE(C0 % 16 == 0, "dcn_sample: C0=%d", C0);
   if ((long long)N * H * W == 0) return PP_OK;
   PP_REQUIRE(N <= 65535 && (long long)H * W * 144 < (1LL << 31), "dcn_sample: %d images of %dx%d exceed the grid limits", N, W, H);
-  const dim3 grid(pp_ceil_div(H * W * 144, TPB), N);
   PPDcnArgs a;
   a.x0 = x0; a.x0_cs = x0_cs; a.x0_co = x0_co; a.C0 = C0;
   a.x1 = x1; a.x1_cs = x1_cs; a.x1_co = x1_co;
@@ -548,7 +547,16 @@ int pp_k_dcn_sample(const __half* x0, int x0_cs, int x0_co, int C0, const __half
       if (handled) return PP_OK;
     }
   }
-  if (C == 128) dcn_sample<8><<<grid, TPB, 0, st>>>(a);
+  return pp_k_dcn_sample_plain(a, st);
+}
+
+int pp_k_dcn_sample_plain(const PPDcnArgs& a, cudaStream_t st) {
+  PP_REQUIRE(a.C == 128 || a.C == 256, "dcn_sample: C=%d must be 128 or 256 (16 offset groups)", a.C);
+  if ((long long)a.N * a.H * a.W == 0) return PP_OK;
+  PP_REQUIRE(a.N <= 65535 && (long long)a.H * a.W * 144 < (1LL << 31), "dcn_sample: %d images of %dx%d exceed the grid limits",
+             a.N, a.W, a.H);
+  const dim3 grid(pp_ceil_div(a.H * a.W * 144, TPB), a.N);
+  if (a.C == 128) dcn_sample<8><<<grid, TPB, 0, st>>>(a);
   else dcn_sample<16><<<grid, TPB, 0, st>>>(a);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;

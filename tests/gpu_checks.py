@@ -396,6 +396,35 @@ def check_composite_exact():
     return res
 
 
+def check_dcn_samplers(timing=False):
+    """TMA-staged tiled sampler == plain L2 sampler, bit for bit (same arithmetic in the same order), on the two shapes
+    of the pipeline: C=256 / |offset| <= 5 (flow completion) and C=128 / 3*tanh + flow (generator), with offsets that also
+    leave the staged box (large flows) and the image."""
+    eng = bare_engine()
+    g = torch.Generator().manual_seed(9)
+    res = {}
+    for tag, (N, H, W, C, mag, fscale) in {"rfc": (2, 45, 80, 256, 5.0, None), "gen": (3, 90, 160, 128, 3.0, 2.5),
+                                           "gen_big_flow": (2, 40, 56, 128, 3.0, 12.0)}.items():
+        x = torch.randn(N, H, W, C, generator=g).half().to(DEV)
+        offs = (torch.randn(N, H, W, 432, generator=g) * 1.5).half().to(DEV)
+        flow = None if fscale is None else (torch.randn(N, H, W, 2, generator=g) * fscale).half().to(DEV)
+        a = eng.op_dcn_sample(x, offs, flow, mag, False)
+        b = eng.op_dcn_sample(x, offs, flow, mag, True)
+        torch.cuda.synchronize()
+        res[tag] = dict(mismatch=int((a != b).sum()), nonzero=float((a != 0).float().mean()), nan=bool(torch.isnan(b.float()).any()))
+        if timing:
+            for name, tl in (("plain", False), ("tiled", True)):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                eng.op_dcn_sample(x, offs, flow, mag, tl)
+                s.record()
+                for _ in range(20):
+                    eng.op_dcn_sample(x, offs, flow, mag, tl)
+                e.record()
+                torch.cuda.synchronize()
+                res[tag][name + "_us"] = s.elapsed_time(e) / 20 * 1000
+    return res
+
+
 def check_step_variants():
     """The recurrent propagation steps have three execution variants -- multi-layer program kernel (default), one launch
     per layer with the TMA-staged deformable sampler, one launch per layer with the plain L2 sampler -- that perform the
@@ -476,7 +505,8 @@ def main():
                ("e2e", lambda: check_e2e(golden)), ("c1_node", lambda: check_c1_node(golden2)),
                ("raft20", lambda: check_raft20(golden2)), ("chunked", lambda: check_chunked(golden2)),
                ("outpaint_node", lambda: check_outpaint_node(golden2)), ("composite_exact", check_composite_exact),
-               ("small_workspace", check_small_workspace_fallback), ("step_variants", check_step_variants)]
+               ("small_workspace", check_small_workspace_fallback), ("step_variants", check_step_variants),
+               ("dcn_samplers", lambda: check_dcn_samplers(True))]
     for name, fn in checks:
         if only and not any(o in name for o in only):
             continue
