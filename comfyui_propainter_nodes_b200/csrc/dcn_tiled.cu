@@ -37,7 +37,7 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
 // threads work through the tile's (pixel, group-in-quad, tap) items from shared memory.  No in-CTA pipeline: latency is
 // hidden by 3-4 resident CTAs per SM and 4x more CTAs than tiles.
 template <int CPG>
-__global__ void __launch_bounds__(NT) dcn_sample_tiled(const __grid_constant__ TiledParams P) {
+__global__ void __launch_bounds__(NT, 2) dcn_sample_tiled(const __grid_constant__ TiledParams P) {
   using namespace ppx;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NT) dcn_sample_tiled(const __grid_constant__ T
   const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
   const int y0 = ty * P.TH, x0 = tx * P.TW;              // tile origin
   const int by0 = y0 - P.R, bx0 = x0 - P.R;              // box origin (may be negative: zero-filled)
-  const int H = a.H, W = a.W, C = a.C;
+  const int H = a.H, W = a.W;
   constexpr int QC = 4 * CPG;                            // channels of a quad
   if (tid == 0) {
     mbar_init(full, 1);
@@ -61,87 +61,29 @@ __global__ void __launch_bounds__(NT) dcn_sample_tiled(const __grid_constant__ T
   __syncthreads();
   mbar_wait(full, 0);
   const int items = P.TH * P.TW * 36;                    // (pixel, group in quad, tap)
-  const long long img_px = (long long)n * H * W;
-  for (int it = tid; it < items; it += NT) {
-    const int gk4 = it % 36, pp = it / 36;
-    const int gq = gk4 / 9, k = gk4 - gq * 9;
-    const int g = quad * 4 + gq;
-    const int py_i = pp / P.TW, px_i = pp - py_i * P.TW;
-    const int y = y0 + py_i, x = x0 + px_i;
-    if (y >= H || x >= W) continue;
-    const long long m = img_px + (long long)y * W + x;
-    const __half* o = a.offs + m * a.offs_cs;
-    const int gk = g * 9 + k;
-    float dy = a.max_mag * tanhf(__half2float(o[2 * gk]));
-    float dx = a.max_mag * tanhf(__half2float(o[2 * gk + 1]));
-    if (a.flow != nullptr) {
-      dx += __half2float(a.flow[m * a.flow_cs + a.flow_co]);
-      dy += __half2float(a.flow[m * a.flow_cs + a.flow_co + 1]);
-    }
-    const float mod = 1.f / (1.f + __expf(-__half2float(o[288 + gk])));
-    const float py = (float)(y - 1 + k / 3) + dy, px = (float)(x - 1 + k % 3) + dx;
-    float acc[CPG];
+  constexpr int U = 32 / CPG;                            // independent items per thread and pass (see dcn_sample.cuh)
+  for (int base = tid; base < items; base += NT * U) {
+    PPDcnItem item[U];
+    int gq[U];
 #pragma unroll
-    for (int i = 0; i < CPG; ++i) acc[i] = 0.f;
-    if (py > -1.f && py < (float)H && px > -1.f && px < (float)W) {
-      const float fy = floorf(py), fx = floorf(px);
-      const int yy0 = (int)fy, xx0 = (int)fx;
-      const float ay = py - fy, ax = px - fx;
-      const int ry = yy0 - by0, rx = xx0 - bx0;          // corner (0,0) inside the box?
-      if (ry >= 0 && rx >= 0 && ry + 1 < P.BH && rx + 1 < P.BW) {
-#pragma unroll
-        for (int corner = 0; corner < 4; ++corner) {
-          const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
-          const uint4* vp = reinterpret_cast<const uint4*>(box + ((ry + (corner >> 1)) * P.BW + rx + (corner & 1)) * (QC * 2) +
-                                                            gq * (CPG * 2));
-#pragma unroll
-          for (int v = 0; v < CPG / 8; ++v) {
-            const uint4 qv = vp[v];
-            const __half2* hq = reinterpret_cast<const __half2*>(&qv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(hq[e]);
-              acc[v * 8 + 2 * e] += w * f.x;
-              acc[v * 8 + 2 * e + 1] += w * f.y;
-            }
-          }
-        }
-      } else {
-        // outside the staged box (large flow): same arithmetic from global memory
-        const int c = g * CPG;
-        const __half* src;
-        int cs;
-        if (c < a.C0) { src = a.x0 + a.x0_co + c; cs = a.x0_cs; }
-        else { src = a.x1 + a.x1_co + (c - a.C0); cs = a.x1_cs; }
-        src += img_px * cs;
-#pragma unroll
-        for (int corner = 0; corner < 4; ++corner) {
-          const int yy = yy0 + (corner >> 1), xx = xx0 + (corner & 1);
-          if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-          const float w = ((corner >> 1) ? ay : 1.f - ay) * ((corner & 1) ? ax : 1.f - ax);
-          const uint4* vp = reinterpret_cast<const uint4*>(src + ((long long)yy * W + xx) * cs);
-#pragma unroll
-          for (int v = 0; v < CPG / 8; ++v) {
-            const uint4 qv = vp[v];
-            const __half2* hq = reinterpret_cast<const __half2*>(&qv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(hq[e]);
-              acc[v * 8 + 2 * e] += w * f.x;
-              acc[v * 8 + 2 * e + 1] += w * f.y;
-            }
-          }
-        }
+    for (int u = 0; u < U; ++u) {
+      const int it = base + u * NT;
+      item[u].m = -1;
+      gq[u] = 0;
+      if (it < items) {
+        const int gk4 = it % 36, pp = it / 36;
+        gq[u] = gk4 / 9;
+        const int py_i = pp / P.TW, px_i = pp - py_i * P.TW;
+        const int y = y0 + py_i, x = x0 + px_i;
+        if (y < H && x < W) item[u] = dcn_item_setup<false>(a, n, y * W + x, quad * 4 + gq[u], gk4 - gq[u] * 9);
       }
     }
-    __half* d = a.cols + m * (long long)(9 * C) + k * C + g * CPG;
+    uint4 q[U][4][CPG / 8];
+    float w[U][4];
 #pragma unroll
-    for (int v = 0; v < CPG / 8; ++v) {
-      __align__(16) __half2 h[4];
+    for (int u = 0; u < U; ++u) dcn_item_gather<CPG, false>(a, item[u], box, by0, bx0, P.BH, P.BW, QC, gq[u], q[u], w[u]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(mod * acc[v * 8 + 2 * e], mod * acc[v * 8 + 2 * e + 1]);
-      reinterpret_cast<uint4*>(d)[v] = *reinterpret_cast<uint4*>(h);
-    }
+    for (int u = 0; u < U; ++u) dcn_item_store<CPG>(a, item[u], q[u], w[u]);
   }
 }
 

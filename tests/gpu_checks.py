@@ -459,7 +459,9 @@ def check_step_variants():
                 os.environ[k] = v
     res = {}
     for tag in ("program", "tiled"):
-        res[tag + "_vs_plain"] = [int((a != b).sum()) for a, b in zip(outs[tag], outs["plain"])]
+        # lane 3 of the prediction tensor is never written (3 output channels in a 4-wide pixel): compare rgb only
+        res[tag + "_vs_plain"] = [int((a[..., :3] != b[..., :3]).sum()) if a.dim() == 4 and a.shape[-1] == 4 else int((a != b).sum())
+                                  for a, b in zip(outs[tag], outs["plain"])]
     return res
 
 
