@@ -486,34 +486,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
         const unsigned per_img = (unsigned)(a.H * a.W * 144);
         const unsigned total = per_img * (unsigned)a.N;
         const unsigned stride = G * NUM_EPI_THREADS;
-        // 4 independent items per pass: their offset loads and corner gathers overlap (one item is a chain of two
-        // dependent L2 round trips, and there are only 256 sampling threads per SM here)
+        // the sampling is bound by L1 wavefronts (one per uncoalesced 16/32-byte gather), not by latency: a two-phase
+        // batched form (all offsets first, then all gathers) measured slower (78 vs 52 us per layer)
         for (unsigned idx = blockIdx.x * NUM_EPI_THREADS + tid; idx < total; idx += 4 * stride) {
-          PPDcnItem items[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {       // phase 1: offsets / modulation of 4 items
+          for (int u = 0; u < 4; ++u) {
             const unsigned i2 = idx + u * stride;
-            items[u].m = -1;
             if (i2 < total) {
-              const unsigned n = i2 / per_img, r2 = i2 - n * per_img;
-              const int gk = (int)(r2 % 144u);
-              items[u] = dcn_item_setup<true>(a, (int)n, (int)(r2 / 144u), gk / 9, gk % 9);
+              const unsigned n = i2 / per_img;
+              if (a.C == 128) dcn_sample_item<8, true>(a, i2 - n * per_img, (int)n);
+              else dcn_sample_item<16, true>(a, i2 - n * per_img, (int)n);
             }
-          }
-          if (a.C == 128) {
-            uint4 q[4][4][1];
-            float w[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dcn_item_gather<8, true>(a, items[u], nullptr, 0, 0, 0, 0, 0, 0, q[u], w[u]);   // phase 2
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dcn_item_store<8>(a, items[u], q[u], w[u]);                                       // phase 3
-          } else {
-            uint4 q[4][4][2];
-            float w[4][4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dcn_item_gather<16, true>(a, items[u], nullptr, 0, 0, 0, 0, 0, 0, q[u], w[u]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dcn_item_store<16>(a, items[u], q[u], w[u]);
           }
         }
       } else {
