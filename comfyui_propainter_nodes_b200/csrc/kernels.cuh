@@ -20,6 +20,7 @@ int pp_k_copy_blocks(void* dst, const int* dst_idx_dev, const void* src, const i
                      long long block_bytes, cudaStream_t st);
 
 // ---- RAFT (kernels_raft.cu) ---------------------------------------------------------------------
+size_t pp_k_instnorm_scratch_floats(int N, int HW, int C);
 int pp_k_instnorm_stats(const __half* x, int N, int HW, int C, float* sums /*[N][2][C]*/, cudaStream_t st);
 int pp_k_instnorm_apply(const __half* x, const float* sums, const __half* residual, __half* out, int N, int HW, int C,
                         int relu, cudaStream_t st);

@@ -12,32 +12,51 @@ inline int nblocks(long long n, int per = TPB) { return (int)((n + per - 1) / pe
 // grid (chunks, N); block = 256 threads; thread t owns channel pair (t % (C/2)) and strides pixels.
 // (reference: RAFT/extractor.py fnet norm layers, F.instance_norm eps=1e-5, biased variance)
 // ------------------------------------------------------------------------------------------------
+// Deterministic: no floating-point atomics.  A block reduces its pixel lanes in lane order, writes its partial sums to
+// `partial[n][block][2C]`, and the block that arrives last (integer counter) adds the partials in block order -- the
+// result does not depend on scheduling, so RAFT (and everything after it) is bit-reproducible run to run and between
+// the single-GPU and the sharded multi-GPU execution.
 __global__ void instnorm_stats(const __half* __restrict__ x, int HW, int C, float* __restrict__ sums,
-                               int pix_per_block) {
-  extern __shared__ float sm[];  // [2][C]
+                               float* __restrict__ partial, unsigned int* __restrict__ counters, int pix_per_block) {
+  extern __shared__ float sm[];  // [lanes][2C]
+  __shared__ bool last;
   const int n = blockIdx.y;
   const int C2 = C >> 1;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const int lanes = blockDim.x / C2;  // pixel lanes per block
   const int cp = threadIdx.x % C2;
   const int pl = threadIdx.x / C2;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
   if (pl < lanes) {
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
     const __half2* base = reinterpret_cast<const __half2*>(x + ((long long)n * HW) * C) + cp;
     for (int p = p0 + pl; p < p1; p += lanes) {
       const float2 v = __half22float2(base[(long long)p * C2]);
       s0 += v.x; s1 += v.y; q0 += v.x * v.x; q1 += v.y * v.y;
     }
-    atomicAdd(&sm[2 * cp], s0);
-    atomicAdd(&sm[2 * cp + 1], s1);
-    atomicAdd(&sm[C + 2 * cp], q0);
-    atomicAdd(&sm[C + 2 * cp + 1], q1);
+    float* row = sm + pl * 2 * C;
+    row[2 * cp] = s0; row[2 * cp + 1] = s1; row[C + 2 * cp] = q0; row[C + 2 * cp + 1] = q1;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[(long long)n * 2 * C + i], sm[i]);
+  float* mine = partial + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += sm[l * 2 * C + i];
+    mine[i] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&counters[n], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    const float* all = partial + (long long)n * gridDim.x * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float acc = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(all + (long long)b * 2 * C + i);
+      sums[(long long)n * 2 * C + i] = acc;
+    }
+  }
 }
 
 // out = [relu]( (x - mean) * rstd );  if residual: out = relu(residual + out)   (ResidualBlock tail)
@@ -257,12 +276,21 @@ __global__ void convex_upsample(const float* __restrict__ coords1, const __half*
 
 }  // namespace
 
+size_t pp_k_instnorm_scratch_floats(int N, int HW, int C) {
+  return (size_t)N * 2 * C * (pp_ceil_div(HW, 1024) + 1) + (size_t)N + 64;
+}
+
+// sums: scratch of pp_k_instnorm_scratch_floats(N, HW, C) floats; the statistics [N][2][C] are its first N*2*C entries
 int pp_k_instnorm_stats(const __half* x, int N, int HW, int C, float* sums, cudaStream_t st) {
-  PP_REQUIRE(C % 2 == 0 && C <= 512, "instnorm: unsupported C=%d", C);
-  PP_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)N * 2 * C * sizeof(float), st));
+  PP_REQUIRE(C % 2 == 0 && C <= 256, "instnorm: unsupported C=%d", C);
   const int pix_per_block = 1024;
-  dim3 grid(pp_ceil_div(HW, pix_per_block), N);
-  instnorm_stats<<<grid, 256, 2 * C * sizeof(float), st>>>(x, HW, C, sums, pix_per_block);
+  const int nblk = pp_ceil_div(HW, pix_per_block);
+  float* partial = sums + (size_t)N * 2 * C;
+  unsigned int* counters = reinterpret_cast<unsigned int*>(partial + (size_t)N * nblk * 2 * C);
+  PP_CUDA_CHECK(cudaMemsetAsync(counters, 0, (size_t)N * sizeof(unsigned int), st));
+  dim3 grid(nblk, N);
+  const int lanes = 256 / (C / 2);
+  instnorm_stats<<<grid, 256, (size_t)lanes * 2 * C * sizeof(float), st>>>(x, HW, C, sums, partial, counters, pix_per_block);
   PP_CUDA_CHECK(cudaGetLastError());
   return PP_OK;
 }

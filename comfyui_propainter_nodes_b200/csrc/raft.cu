@@ -119,7 +119,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
     __half* x8;
     float* sums;
     PP_TRY(pp_alloc(e, &x8, (size_t)chunk * H * W * 8, "raft input"));
-    PP_TRY(pp_alloc(e, &sums, (size_t)chunk * 2 * 256, "instnorm sums"));
+    PP_TRY(pp_alloc(e, &sums, pp_k_instnorm_scratch_floats(chunk, (H / 2) * (W / 2), 256), "instnorm sums"));
     for (int f0 = 0; f0 < T; f0 += chunk) {
       const int n = (f0 + chunk <= T) ? chunk : T - f0;
       PP_TRY(pp_k_nchw_f32_to_nhwc_f16(frames + (size_t)f0 * 3 * H * W, x8, n, 3, H, W, 8, 0, 8, st));

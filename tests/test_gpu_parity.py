@@ -98,9 +98,14 @@ def test_fullsize_flow_completion_keeps_known_flow(C):
     keep_b = (masks[1:] == 0).expand_as(fb)
     assert torch.equal(ob[keep_b], fb[keep_b])
     assert torch.isfinite(of).all() and torch.isfinite(ob).all()
-    # determinism: same inputs -> bit-identical outputs
+    # determinism: same inputs -> bit-identical outputs (RAFT included: instance-norm statistics use no float atomics)
     of2, _ = eng.flow_complete(ff, fb, masks)
     assert torch.equal(of, of2)
+    ff2, fb2 = eng.raft_bidir(frames, 2)
+    assert torch.equal(ff, ff2) and torch.equal(fb, fb2)
+    # and independent of how the pairs are batched (a shard of the pairs gives the same flows)
+    ff3, fb3 = eng.raft_bidir(frames[1:3], 2)
+    assert torch.equal(ff3[0], ff[1]) and torch.equal(fb3[0], fb[1])
 
 
 def test_fullsize_image_propagation_identities(C):
