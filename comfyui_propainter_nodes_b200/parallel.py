@@ -108,7 +108,15 @@ def inpaint_clip_distributed(models, frames, flow_masks, masks_dilated, orig_u8,
     T = cfg.video_length
     H, W = frames.shape[-2:]
     dev = eng.device
+    marks = []          # PP_DIST_TIMING=1: CUDA events between the stages, printed by rank 0
 
+    def mark(name):
+        if os.environ.get("PP_DIST_TIMING"):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     # ---- RAFT: pairs [lo, hi) need frames [lo, hi]; every rank writes its shard into the full buffers, one
     #      all-gather per direction completes them (fp32: the N-GPU flows equal the 1-GPU flows bit for bit)
     n_pairs = T - 1
@@ -117,15 +125,19 @@ def inpaint_clip_distributed(models, frames, flow_masks, masks_dilated, orig_u8,
     fb = torch.empty_like(ff)
     if hi > lo:
         eng.raft_bidir(frames[0, lo:hi + 1], cfg.raft_iter, out=(ff[lo:hi], fb[lo:hi]))
+    mark("raft")
     sizes = shard_sizes(n_pairs, world)
     gather_rows(eng, ff, sizes, 0, group)
     gather_rows(eng, fb, sizes, 0, group)
+    mark("gather_flows")
     dt = torch.float16 if cfg.use_half else torch.float32
     gt = (ff.unsqueeze(0).to(dt), fb.unsqueeze(0).to(dt))
 
     # ---- recurrent stages (serial in time): see complete_flow_distributed
     pred = complete_flow_distributed(models.flow_model, gt, flow_masks, cfg.subvideo_length, rank, world, group)
+    mark("flow_completion")
     uf, um = PI.image_propagation(models.inpaint_model, frames, masks_dilated, pred, cfg)
+    mark("image_propagation")
 
     # ---- generator windows: contiguous ranges; each rank encodes only the frames its windows touch and writes its
     #      predictions into the full buffer, one all-gather completes it
@@ -142,7 +154,9 @@ def inpaint_clip_distributed(models, frames, flow_masks, masks_dilated, orig_u8,
             preds[o:o + wsizes[rank]] = eng.gen_run(sched[wlo:whi])
         finally:
             eng.gen_end()
+    mark("generator_windows")
     gather_rows(eng, preds, wsizes, 0, group)
+    mark("gather_predictions")
 
     ids, first = composite_order(sched)
     ids_dev = torch.tensor(ids, dtype=torch.int32, device=dev)
