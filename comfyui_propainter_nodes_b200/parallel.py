@@ -16,6 +16,8 @@ The collective payloads are small next to the compute (flows 2x[T-1,2,H,W] fp32,
 """
 from __future__ import annotations
 
+import os
+import sys
 from typing import List, Sequence, Tuple
 
 import torch
@@ -168,6 +170,11 @@ def inpaint_clip_distributed(models, frames, flow_masks, masks_dilated, orig_u8,
         n = len(nb)
         eng.composite(preds[o:o + n], md, orig, comp, ids_dev[o:o + n], first_dev[o:o + n], cfg.use_half)
         o += n
+    mark("composite")
+    if marks and rank == 0:
+        torch.cuda.synchronize()
+        print("[dist timing, rank 0, ms] " + " ".join(f"{b[0]}={a[1].elapsed_time(b[1]):.2f}" for a, b in zip(marks, marks[1:])),
+              file=sys.stderr, flush=True)
     return comp
 
 
