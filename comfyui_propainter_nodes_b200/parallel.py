@@ -71,6 +71,39 @@ def window_shards(n_windows: int, world: int) -> List[Tuple[int, int]]:
     return [shard_range(n_windows, world, r) for r in range(world)]
 
 
+def balanced_ranges(costs: Sequence[float], world: int) -> List[Tuple[int, int]]:
+    """Contiguous partition of range(len(costs)) into `world` (possibly empty) ranges minimising the largest range sum
+    (exact, dynamic programming over prefix sums).  Used for the sliding windows: they differ in length (6..11 local
+    frames, 3..9 reference frames), and the rank with the heaviest share sets the time of the exchange that follows."""
+    n = len(costs)
+    pre = [0.0]
+    for c in costs:
+        pre.append(pre[-1] + float(c))
+    INF = float("inf")
+    # best[k][i] = minimal possible max-load when the first i items are split into k ranges
+    best = [[INF] * (n + 1) for _ in range(world + 1)]
+    cut = [[0] * (n + 1) for _ in range(world + 1)]
+    best[0][0] = 0.0
+    for k in range(1, world + 1):
+        for i in range(n + 1):
+            for j in range(i + 1):
+                v = max(best[k - 1][j], pre[i] - pre[j])
+                if v < best[k][i]:
+                    best[k][i], cut[k][i] = v, j
+    out, i = [], n
+    for k in range(world, 0, -1):
+        j = cut[k][i]
+        out.append((j, i))
+        i = j
+    return out[::-1]
+
+
+def window_cost(nb, refs) -> float:
+    """Relative cost of one sliding window: the transformer / attention / SoftSplit work grows with all t frames, the
+    feature propagation, decoder and encoder of new frames with the local ones."""
+    return float(len(nb) + len(refs)) + 1.5 * float(len(nb))
+
+
 def composite_order(schedule) -> Tuple[List[int], List[int]]:
     """Flat (frame id, first-visit flag) lists of the composite, in window order (propainter_inference.py:294-307)."""
     seen, ids, first = set(), [], []
@@ -144,9 +177,10 @@ def inpaint_clip_distributed(models, frames, flow_masks, masks_dilated, orig_u8,
     # ---- generator windows: contiguous ranges; each rank encodes only the frames its windows touch and writes its
     #      predictions into the full buffer, one all-gather completes it
     sched = PI.window_schedule(cfg)
-    wlo, whi = shard_range(len(sched), world, rank)
+    wranges = balanced_ranges([window_cost(nb, refs) for nb, refs in sched], world)
+    wlo, whi = wranges[rank]
     md = masks_dilated[0].to(device=dev, dtype=torch.float32).contiguous()
-    wsizes = [sum(len(nb) for nb, _ in sched[a:b]) for a, b in window_shards(len(sched), world)]
+    wsizes = [sum(len(nb) for nb, _ in sched[a:b]) for a, b in wranges]
     preds = torch.empty(sum(wsizes), H, W, 4, device=dev, dtype=torch.float16)
     if whi > wlo:
         need = sorted({i for nb, refs in sched[wlo:whi] for i in list(nb) + list(refs)})

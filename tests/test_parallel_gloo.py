@@ -94,3 +94,20 @@ def test_flow_chunks_and_teams():
             n_teams, size = P.flow_teams(n_chunks, world)
             assert 1 <= n_teams <= n_chunks and size >= 1 and n_teams * size <= world
     assert P.flow_teams(1, 8) == (1, 8) and P.flow_teams(3, 8) == (3, 2) and P.flow_teams(3, 2) == (2, 1)
+
+
+def test_balanced_ranges_minimise_the_heaviest_share():
+    import itertools
+    for costs, world in (([1, 1, 1, 1], 2), ([5, 1, 1, 1, 1, 1], 2), ([3, 3, 3, 9, 1, 1, 1], 3), ([2] * 16, 8), ([7], 4), ([], 3)):
+        parts = P.balanced_ranges(costs, world)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == len(costs)
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        got = max(sum(costs[a:b]) for a, b in parts) if costs else 0
+        # brute force over all cut positions
+        best = min((max(sum(costs[a:b]) for a, b in zip((0,) + c, c + (len(costs),)))
+                    for c in itertools.combinations_with_replacement(range(len(costs) + 1), world - 1)), default=0) if costs else 0
+        assert abs(got - best) < 1e-9, (costs, world, parts)
+    sched = O.window_schedule(80, 10, 10, 80)
+    parts = P.balanced_ranges([P.window_cost(nb, r) for nb, r in sched], 8)
+    loads = [sum(P.window_cost(*w) for w in sched[a:b]) for a, b in parts]
+    assert max(loads) <= 1.25 * (sum(loads) / 8)
