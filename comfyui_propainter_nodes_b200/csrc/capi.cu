@@ -1,5 +1,9 @@
 // extern "C" surface of libpropainter_b200.so (declared in include/propainter_b200.h).
+#include <math.h>
 #include <string.h>
+
+#include <thread>
+#include <vector>
 
 #include "../../include/propainter_b200.h"
 #include "dcn_sample.cuh"
@@ -252,6 +256,38 @@ int pp_preprocess(pp_handle h, const float* image, const float* mask, int mask_f
   return PP_OK;
 }
 
+// Shared tail of the pre-processing entry points: 8-bit frames / masks at the input size -> outputs at the processing size
+static int preprocess_from_u8(PPEngine& e, const uint8_t* u8_in, const uint8_t* m_in, int mask_frames, int T, int H, int W,
+                              int out_h, int out_w, int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8, float* frames,
+                              float* flow_masks, float* masks_dilated, cudaStream_t st) {
+  const bool resize = out_h != H || out_w != W;
+  const uint8_t* m_use = m_in;
+  if (resize) {
+    const size_t mid_px = (size_t)T * H * out_w;
+    uint8_t *tmp, *m_out;
+    int* coef;
+    const int mx = out_h > out_w ? out_h : out_w;
+    const double sc = fmax(fmax((double)H / out_h, (double)W / out_w), 1.0);
+    const size_t coef_ints = 2 * (size_t)mx * ((size_t)ceil(2.0 * sc) * 2 + 1 + 2) + 64;
+    PP_TRY(pp_alloc(e, &tmp, mid_px * 3, "resize pass 1"));
+    PP_TRY(pp_alloc(e, &m_out, (size_t)mask_frames * out_h * out_w, "mask resized"));
+    PP_TRY(pp_alloc(e, &coef, coef_ints, "resize coefficients"));
+    // frames: bicubic on the 8-bit image (image_utils.py:98-103); masks: the 8-bit 'L' image the same way (:142-150)
+    PP_TRY(pp_k_resize_bicubic_u8(u8_in, orig_u8, tmp, coef, coef_ints, T, H, W, 3, out_h, out_w, st));
+    PP_TRY(pp_k_resize_bicubic_u8(m_in, m_out, tmp, coef, coef_ints, mask_frames, H, W, 1, out_h, out_w, st));
+    m_use = m_out;
+    e.launches += 4;
+  } else {
+    PP_CUDA_CHECK(cudaMemcpyAsync(orig_u8, u8_in, (size_t)T * H * W * 3, cudaMemcpyDeviceToDevice, st));
+  }
+  PP_TRY(pp_k_u8_to_frames(orig_u8, frames, T, out_h, out_w, st));                       // u8/255*2-1 (:186-190)
+  // any non-zero -> dilations (image_utils.py:152-170)
+  PP_TRY(pp_k_dilate_masks_u8(m_use, mask_frames, T, out_h, out_w, flow_mask_dilates, mask_dilates, flow_masks,
+                              masks_dilated, st));
+  e.launches += 3;
+  return PP_OK;
+}
+
 int pp_preprocess_resize(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
                          int out_h, int out_w, int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8, float* frames,
                          float* flow_masks, float* masks_dilated, void* stream) {
@@ -260,27 +296,51 @@ int pp_preprocess_resize(pp_handle h, const float* image, const float* mask, int
   PP_REQUIRE(out_h > 0 && out_w > 0 && H > 0 && W > 0, "pp_preprocess_resize: bad size");
   ArenaGuard guard(e.arena);
   cudaStream_t st = as_stream(stream);
-  const size_t in_px = (size_t)T * H * W, mid_px = (size_t)T * H * out_w;
-  uint8_t *u8_in, *tmp, *m_in, *m_out;
-  int* coef;
-  const int mx = out_h > out_w ? out_h : out_w;
-  const double sc = fmax(fmax((double)H / out_h, (double)W / out_w), 1.0);
-  const size_t coef_ints = 2 * (size_t)mx * ((size_t)ceil(2.0 * sc) * 2 + 1 + 2) + 64;
+  const size_t in_px = (size_t)T * H * W;
+  uint8_t *u8_in, *m_in;
   PP_TRY(pp_alloc(e, &u8_in, in_px * 3, "resize input"));
-  PP_TRY(pp_alloc(e, &tmp, mid_px * 3, "resize pass 1"));
   PP_TRY(pp_alloc(e, &m_in, (size_t)mask_frames * H * W, "mask input"));
-  PP_TRY(pp_alloc(e, &m_out, (size_t)mask_frames * out_h * out_w, "mask resized"));
-  PP_TRY(pp_alloc(e, &coef, coef_ints, "resize coefficients"));
-  // frames: float -> uint8 (truncate) -> bicubic -> originals + [-1,1] tensor (image_utils.py:106-114, 98-103, 186-190)
+  // float -> uint8 (truncate) for the frames (image_utils.py:106-114) and the mask images (:128-134)
   PP_TRY(pp_k_quantize_u8(image, u8_in, (long long)in_px * 3, st));
-  PP_TRY(pp_k_resize_bicubic_u8(u8_in, orig_u8, tmp, coef, coef_ints, T, H, W, 3, out_h, out_w, st));
-  PP_TRY(pp_k_u8_to_frames(orig_u8, frames, T, out_h, out_w, st));
-  // masks: float -> 8-bit 'L' image -> bicubic -> any non-zero -> dilations (image_utils.py:128-170)
   PP_TRY(pp_k_quantize_u8(mask, m_in, (long long)mask_frames * H * W, st));
-  PP_TRY(pp_k_resize_bicubic_u8(m_in, m_out, tmp, coef, coef_ints, mask_frames, H, W, 1, out_h, out_w, st));
-  PP_TRY(pp_k_dilate_masks_u8(m_out, mask_frames, T, out_h, out_w, flow_mask_dilates, mask_dilates, flow_masks,
-                              masks_dilated, st));
-  e.launches += 9;
+  e.launches += 2;
+  return preprocess_from_u8(e, u8_in, m_in, mask_frames, T, H, W, out_h, out_w, flow_mask_dilates, mask_dilates, orig_u8,
+                            frames, flow_masks, masks_dilated, st);
+}
+
+int pp_preprocess_u8(pp_handle h, const uint8_t* image_u8, const uint8_t* mask_u8, int mask_frames, int T, int H, int W,
+                     int out_h, int out_w, int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8, float* frames,
+                     float* flow_masks, float* masks_dilated, void* stream) {
+  PP_HANDLE(h);
+  PP_REQUIRE(image_u8 && mask_u8 && orig_u8 && frames && flow_masks && masks_dilated, "pp_preprocess_u8: null pointer");
+  PP_REQUIRE(out_h > 0 && out_w > 0 && H > 0 && W > 0, "pp_preprocess_u8: bad size");
+  ArenaGuard guard(e.arena);
+  return preprocess_from_u8(e, image_u8, mask_u8, mask_frames, T, H, W, out_h, out_w, flow_mask_dilates, mask_dilates,
+                            orig_u8, frames, flow_masks, masks_dilated, as_stream(stream));
+}
+
+// Host helper (no GPU involved): float [0,1] -> uint8 with the reference's arithmetic -- x * 255 in float32, clip to
+// [0, 255], truncate (utils/image_utils.py:106-114, 128-134) -- on `threads` host threads.  Lets a host caller ship 1/4 of
+// the bytes over PCIe: quantise straight into a page-locked staging buffer, copy, then pp_preprocess_u8.
+int pp_host_quantize_u8(const float* src, uint8_t* dst, long long n, int threads) {
+  PP_REQUIRE(src != nullptr && dst != nullptr && n >= 0, "pp_host_quantize_u8: bad argument");
+  if (threads < 1) threads = 1;
+  if (threads > 64) threads = 64;
+  auto work = [=](long long lo, long long hi) {
+    for (long long i = lo; i < hi; ++i) {
+      float v = src[i] * 255.0f;
+      v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);     // NaN compares false twice and converts to 0 like the device path
+      dst[i] = (uint8_t)(int)v;
+    }
+  };
+  if (threads == 1 || n < (1 << 16)) { work(0, n); return PP_OK; }
+  std::vector<std::thread> pool;
+  const long long per = (n + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    const long long lo = t * per, hi = lo + per < n ? lo + per : n;
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
   return PP_OK;
 }
 

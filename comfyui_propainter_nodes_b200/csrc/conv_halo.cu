@@ -46,6 +46,8 @@ struct HaloParams {
   int BW, BH;        // patch size in pixels
   int tiles_x, tiles_y, n_tiles;
   int a_stage_bytes, b_stage_bytes, SA, SB;
+  int tps;           // filter taps per weight stage: narrow N tiles pack several taps' [BN x 64] tiles into one stage, so
+                     // the MMA issuer waits / commits once per group instead of once per tap (it is issue-bound there)
   int accw;          // TMEM columns per accumulator
   int chunks;        // Cin / 64
   int flat;          // 1x1 convs: tiles are runs of 128*MT consecutive pixels of the flattened [N*H*W] pixel list
@@ -310,11 +312,15 @@ __global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_
         const uint32_t bytes = (uint32_t)(min(p.BN, p.Cout_g_pad - n0) * 128);
         const __half* wbase = p.wpacked + ((long long)t.g * p.num_kc * p.Cout_g_pad + n0) * 64;
         for (int c = 0; c < h.chunks; ++c) {
-          for (int tap = 0; tap < taps; ++tap) {
-            const int kc = tap * h.chunks + c;
+          for (int tap0 = 0; tap0 < taps; tap0 += h.tps) {
+            const int tn = min(h.tps, taps - tap0);
             mbar_wait(&b_empty[s], phase ^ 1);
-            mbar_arrive_expect_tx(&b_full[s], bytes);
-            bulk_g2s(smem_u32(smem_b + s * h.b_stage_bytes), wbase + (long long)kc * p.Cout_g_pad * 64, bytes, &b_full[s]);
+            mbar_arrive_expect_tx(&b_full[s], bytes * (uint32_t)tn);
+            for (int t = 0; t < tn; ++t) {
+              const int kc = (tap0 + t) * h.chunks + c;
+              bulk_g2s(smem_u32(smem_b + s * h.b_stage_bytes + t * p.BN * 128), wbase + (long long)kc * p.Cout_g_pad * 64, bytes,
+                       &b_full[s]);
+            }
             if (++s == h.SB) { s = 0; phase ^= 1; }
           }
         }
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_
       const uint32_t step_x = (uint32_t)p.dw * 8;                                           // next tap in the row
       const uint32_t step_row = (uint32_t)(p.dh * h.BW - (p.kw - 1) * p.dw) * 8;            // last tap of a row -> next row
       const uint32_t sub16 = (uint32_t)h.sub_bytes >> 4;
+      const uint32_t tap16 = (uint32_t)p.BN * 8;                                            // next tap's weight tile in the stage
       const bool two = h.MT == 2;
       const int kw = p.kw;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -351,26 +358,30 @@ __global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_
           tc_fence_after();
           uint64_t adesc = a_hi | (uint64_t)(a_base0 + sa * a_stage16);
           int kx = 0;
-          for (int tap = 0; tap < taps; ++tap) {
+          for (int tap0 = 0; tap0 < taps; tap0 += h.tps) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
-            const uint64_t bdesc = b_hi | (uint64_t)(b_base0 + sb * b_stage16);
-            umma_f16(d0, adesc, bdesc, idesc, accum);
-            umma_f16(d0, adesc + 2, bdesc + 2, idesc, 1u);
-            umma_f16(d0, adesc + 4, bdesc + 4, idesc, 1u);
-            umma_f16(d0, adesc + 6, bdesc + 6, idesc, 1u);
-            if (two) {
-              const uint64_t adesc1 = adesc + sub16;
-              umma_f16(d1, adesc1, bdesc, idesc, accum);
-              umma_f16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
-              umma_f16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
-              umma_f16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+            uint64_t bdesc = b_hi | (uint64_t)(b_base0 + sb * b_stage16);
+            const int tn = min(h.tps, taps - tap0);
+            for (int t = 0; t < tn; ++t) {
+              umma_f16(d0, adesc, bdesc, idesc, accum);
+              umma_f16(d0, adesc + 2, bdesc + 2, idesc, 1u);
+              umma_f16(d0, adesc + 4, bdesc + 4, idesc, 1u);
+              umma_f16(d0, adesc + 6, bdesc + 6, idesc, 1u);
+              if (two) {
+                const uint64_t adesc1 = adesc + sub16;
+                umma_f16(d1, adesc1, bdesc, idesc, accum);
+                umma_f16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                umma_f16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                umma_f16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+              }
+              accum = 1u;
+              bdesc += tap16;
+              adesc += step_x;
+              if (++kx == kw) { kx = 0; adesc += step_row - step_x; }
             }
-            accum = 1u;
             umma_commit(&b_empty[sb]);
             if (++sb == h.SB) { sb = 0; pb ^= 1; }
-            adesc += step_x;
-            if (++kx == kw) { kx = 0; adesc += step_row - step_x; }
           }
           umma_commit(&a_empty[sa]);
           if (++sa == h.SA) { sa = 0; pa ^= 1; }
@@ -623,11 +634,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
           const uint32_t bytes = (uint32_t)(min(p.BN, p.Cout_g_pad - n0) * 128);
           const __half* wbase = p.wpacked + ((long long)t.g * p.num_kc * p.Cout_g_pad + n0) * 64;
           for (int c = 0; c < h.chunks; ++c) {
-            for (int tap = 0; tap < taps; ++tap) {
-              const int kc = tap * h.chunks + c;
+            for (int tap0 = 0; tap0 < taps; tap0 += h.tps) {
+              const int tn = min(h.tps, taps - tap0);
               mbar_wait(&b_empty[s], phase ^ 1);
-              mbar_arrive_expect_tx(&b_full[s], bytes);
-              bulk_g2s(smem_u32(smem_b + s * P.b_stage_bytes), wbase + (long long)kc * p.Cout_g_pad * 64, bytes, &b_full[s]);
+              mbar_arrive_expect_tx(&b_full[s], bytes * (uint32_t)tn);
+              for (int t = 0; t < tn; ++t) {
+                const int kc = (tap0 + t) * h.chunks + c;
+                bulk_g2s(smem_u32(smem_b + s * P.b_stage_bytes + t * p.BN * 128), wbase + (long long)kc * p.Cout_g_pad * 64, bytes,
+                         &b_full[s]);
+              }
               if (++s == P.SB) { s = 0; phase ^= 1; }
             }
           }
@@ -653,6 +668,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
         const uint32_t step_x = (uint32_t)p.dw * 8;
         const uint32_t step_row = (uint32_t)(p.dh * h.BW - (p.kw - 1) * p.dw) * 8;
         const uint32_t sub16 = (uint32_t)h.sub_bytes >> 4;
+        const uint32_t tap16 = (uint32_t)p.BN * 8;
         const bool two = h.MT == 2;
         const int kw = p.kw;
         for (int tile = blockIdx.x; tile < total_tiles; tile += G, ++it) {
@@ -668,26 +684,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_prog_kernel(const __grid_
             tc_fence_after();
             uint64_t adesc = a_hi | (uint64_t)(a_base0 + sa * a_stage16);
             int kx = 0;
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap0 = 0; tap0 < taps; tap0 += h.tps) {
               mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-              const uint64_t bdesc = b_hi | (uint64_t)(b_base0 + sb * b_stage16);
-              umma_f16(d0, adesc, bdesc, idesc, accum);
-              umma_f16(d0, adesc + 2, bdesc + 2, idesc, 1u);
-              umma_f16(d0, adesc + 4, bdesc + 4, idesc, 1u);
-              umma_f16(d0, adesc + 6, bdesc + 6, idesc, 1u);
-              if (two) {
-                const uint64_t adesc1 = adesc + sub16;
-                umma_f16(d1, adesc1, bdesc, idesc, accum);
-                umma_f16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
-                umma_f16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
-                umma_f16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+              uint64_t bdesc = b_hi | (uint64_t)(b_base0 + sb * b_stage16);
+              const int tn = min(h.tps, taps - tap0);
+              for (int t = 0; t < tn; ++t) {
+                umma_f16(d0, adesc, bdesc, idesc, accum);
+                umma_f16(d0, adesc + 2, bdesc + 2, idesc, 1u);
+                umma_f16(d0, adesc + 4, bdesc + 4, idesc, 1u);
+                umma_f16(d0, adesc + 6, bdesc + 6, idesc, 1u);
+                if (two) {
+                  const uint64_t adesc1 = adesc + sub16;
+                  umma_f16(d1, adesc1, bdesc, idesc, accum);
+                  umma_f16(d1, adesc1 + 2, bdesc + 2, idesc, 1u);
+                  umma_f16(d1, adesc1 + 4, bdesc + 4, idesc, 1u);
+                  umma_f16(d1, adesc1 + 6, bdesc + 6, idesc, 1u);
+                }
+                accum = 1u;
+                bdesc += tap16;
+                adesc += step_x;
+                if (++kx == kw) { kx = 0; adesc += step_row - step_x; }
               }
-              accum = 1u;
               umma_commit(&b_empty[sb]);
               if (++sb == P.SB) { sb = 0; pb ^= 1; }
-              adesc += step_x;
-              if (++kx == kw) { kx = 0; adesc += step_row - step_x; }
             }
             umma_commit(&a_empty[sa]);
             if (++sa == P.SA) { sa = 0; pa ^= 1; }
@@ -812,7 +832,17 @@ int halo_configure(const PPConvParams& pin, HaloParams& h, bool one_wave) {
   h.chunks = pp_ceil_div(p.Cin, 64);
   h.accw = pp_ceil_div(bn, 32) * 32;
   h.a_stage_bytes = pp_ceil_div(h.BW * h.BH * 128, 1024) * 1024;
-  h.b_stage_bytes = bn * 128;
+  {
+    // narrow N tiles: several filter taps per weight stage (<= 16 KB), see HaloParams::tps
+    static int max_tps = -1;
+    if (max_tps < 0) { const char* e = getenv("PP_HALO_TPS"); max_tps = e != nullptr ? atoi(e) : 9; }
+    int tps = 16384 / (bn * 128);
+    if (tps > p.kh * p.kw) tps = p.kh * p.kw;
+    if (tps > max_tps) tps = max_tps;
+    if (tps < 1 || p.ups2x) tps = 1;
+    h.tps = tps;
+  }
+  h.b_stage_bytes = h.tps * bn * 128;
   h.ups = p.ups2x ? 1 : 0;
   h.LH = p.H / 2; h.LW = p.W / 2;
   h.LBW = (h.BW - 1) / 2 + 3; h.LBH = (h.BH - 1) / 2 + 3;      // low-res pixels that can feed BW x BH hi-res ones

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "pp_composite": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "pp_preprocess": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "pp_preprocess_resize": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "pp_preprocess_u8": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "pp_host_quantize_u8": (_I, [_VP, _VP, _LL, _I]),
     "pp_postprocess": (_I, [_VP, _VP, _VP, _LL, _VP]),
     "pp_launch_count": (_LL, [_VP]),
     "pp_workspace_peak": (_SZ, [_VP]),
@@ -564,10 +566,14 @@ class Engine:
         image [T,H,W,3] float 0..1, mask [T or 1,H,W] float32 (host or device); ``process_size`` = (width, height) to
         resize to (PIL's 8-bit bicubic resampler, reproduced bit for bit on the device), default: the input size.
         -> frames [1,T,3,h,w], flow_masks [1,T,1,h,w], masks_dilated [1,T,1,h,w] (float32), originals uint8 [T,h,w,3]."""
+        T, H, W, _ = image.shape
+        ow, oh = (W, H) if process_size is None else (int(process_size[0]), int(process_size[1]))
+        if image.device.type == "cpu" and mask.device.type == "cpu" and image.dtype == torch.float32 and mask.dtype == torch.float32:
+            # host tensors (what ComfyUI hands a node): the float -> uint8 truncation is the first thing the reference does
+            # with them, so do it on the host cores straight into page-locked staging buffers and move 1/4 of the bytes
+            return self._preprocess_host(image.contiguous(), mask.contiguous(), flow_mask_dilates, mask_dilates, ow, oh)
         img = image.to(self.device, torch.float32, non_blocking=True).contiguous()
         msk = mask.to(self.device, torch.float32, non_blocking=True).contiguous()
-        T, H, W, _ = img.shape
-        ow, oh = (W, H) if process_size is None else (int(process_size[0]), int(process_size[1]))
         orig = torch.empty(T, oh, ow, 3, device=self.device, dtype=torch.uint8)
         frames = torch.empty(T, 3, oh, ow, device=self.device, dtype=torch.float32)
         fm = torch.empty(T, 1, oh, ow, device=self.device, dtype=torch.float32)
@@ -580,6 +586,29 @@ class Engine:
             self._check(self.lib.pp_preprocess_resize(self.h, _ptr(img), _ptr(msk), msk.shape[0], T, H, W, oh, ow,
                                                       int(flow_mask_dilates), int(mask_dilates), _ptr(orig), _ptr(frames),
                                                       _ptr(fm), _ptr(md), self._stream()))
+        return frames.unsqueeze(0), fm.unsqueeze(0), md.unsqueeze(0), orig
+
+    def _preprocess_host(self, image, mask, flow_mask_dilates, mask_dilates, ow, oh):
+        T, H, W, _ = image.shape
+        threads = min(os.cpu_count() or 1, int(os.environ.get("PP_HOST_THREADS", 16)))
+        try:
+            img8 = torch.empty(image.shape, dtype=torch.uint8, pin_memory=True)
+            msk8 = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:        # locked-memory limit: pageable staging still moves 1/4 of the bytes
+            img8 = torch.empty(image.shape, dtype=torch.uint8)
+            msk8 = torch.empty(mask.shape, dtype=torch.uint8)
+        self._check(self.lib.pp_host_quantize_u8(_ptr(image), _ptr(img8), image.numel(), threads))
+        img8d = img8.to(self.device, non_blocking=True)
+        self._check(self.lib.pp_host_quantize_u8(_ptr(mask), _ptr(msk8), mask.numel(), threads))
+        msk8d = msk8.to(self.device, non_blocking=True)
+        orig = torch.empty(T, oh, ow, 3, device=self.device, dtype=torch.uint8)
+        frames = torch.empty(T, 3, oh, ow, device=self.device, dtype=torch.float32)
+        fm = torch.empty(T, 1, oh, ow, device=self.device, dtype=torch.float32)
+        md = torch.empty_like(fm)
+        self._check(self.lib.pp_preprocess_u8(self.h, _ptr(img8d), _ptr(msk8d), mask.shape[0], T, H, W, oh, ow,
+                                              int(flow_mask_dilates), int(mask_dilates), _ptr(orig), _ptr(frames), _ptr(fm),
+                                              _ptr(md), self._stream()))
+        self._keep_staging = (img8, msk8)      # the async copies read them; released at the next call
         return frames.unsqueeze(0), fm.unsqueeze(0), md.unsqueeze(0), orig
 
     def postprocess(self, comp_u8: torch.Tensor) -> torch.Tensor:

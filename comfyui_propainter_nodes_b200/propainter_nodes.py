@@ -7,9 +7,10 @@ of 8, not resized back), masks squeezed to [T,h,w] and left on the compute devic
 """
 from __future__ import annotations
 
-import torch
+import os
 
 import numpy as np
+import torch
 
 from .propainter_inference import ProPainterConfig, feature_propagation_device, process_inpainting
 from .utils import image_utils as iu
@@ -66,7 +67,11 @@ def _run(models, frames_t, flow_masks_t, masks_dilated_t, originals_u8, cfg: Pro
     updated_frames, updated_masks, flows = process_inpainting(models, frames_t, flow_masks_t, masks_dilated_t, cfg)
     comp = feature_propagation_device(models.inpaint_model, updated_frames, updated_masks, masks_dilated_t, flows,
                                       originals_u8, cfg)
-    images = _to_host(models.inpaint_model.engine.postprocess(comp))   # IMAGE stays a CPU tensor like the reference's
+    images = models.inpaint_model.engine.postprocess(comp)
+    if os.environ.get("PP_IMAGE_ON_DEVICE", "0") in ("", "0"):
+        images = _to_host(images)          # default: the IMAGE is a CPU tensor like the reference's (handle_output)
+    # PP_IMAGE_ON_DEVICE=1: zero-copy hand-over -- the float32 IMAGE stays in HBM for downstream nodes that take CUDA
+    # tensors (saves the 221 MB device->host copy of an 80-frame 640x360 result, ~9 ms)
     return images, flow_masks_t.squeeze(), masks_dilated_t.squeeze()
 
 

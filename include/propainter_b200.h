@@ -123,6 +123,15 @@ PP_API int pp_preprocess(pp_handle h, const float* image, const float* mask, int
 PP_API int pp_preprocess_resize(pp_handle h, const float* image, const float* mask, int mask_frames, int T, int H, int W,
                                 int out_h, int out_w, int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8,
                                 float* frames, float* flow_masks, float* masks_dilated, void* stream);
+/* The same from 8-bit inputs already on the device (image_u8 [T,H,W,3], mask_u8 [mask_frames,H,W]): what is left of the
+ * pre-processing after the float -> uint8 truncation, which a host can do itself (pp_host_quantize_u8) to move 1/4 of the
+ * bytes over PCIe.  out_h / out_w equal to H / W: no resize. */
+PP_API int pp_preprocess_u8(pp_handle h, const uint8_t* image_u8, const uint8_t* mask_u8, int mask_frames, int T, int H,
+                            int W, int out_h, int out_w, int flow_mask_dilates, int mask_dilates, uint8_t* orig_u8,
+                            float* frames, float* flow_masks, float* masks_dilated, void* stream);
+/* HOST helper, no GPU work: dst[i] = (uint8)trunc(clip(src[i] * 255, 0, 255)) in float32, the reference's conversion
+ * (utils/image_utils.py:106-114, 128-134), on `threads` host threads; src / dst are host pointers. */
+PP_API int pp_host_quantize_u8(const float* src, uint8_t* dst, long long n, int threads);
 /* uint8 frames -> float32 / 255 (reference handle_output, utils/image_utils.py:276-290). */
 PP_API int pp_postprocess(pp_handle h, const uint8_t* comp_u8, float* image_out, long long n, void* stream);
 
