@@ -237,6 +237,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_igemm_kernel(const __grid
 
 }  // namespace
 
+namespace {
+thread_local char g_last_kind = '?';
+}
+char pp_last_conv_kind() { return g_last_kind; }
+
 int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
   PPConvParams p = pin;
   PP_REQUIRE(p.BN >= 16 && p.BN <= 256 && p.BN % 16 == 0, "conv: BN=%d must be a multiple of 16 in [16,256]", p.BN);
@@ -274,8 +279,9 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
                   al32(p.out2, p.out2_cstride, p.out2_coff, 0) && al32(p.pre, p.pre_cstride, p.pre_coff, 0) && (p.epi != PP_EPI_GRU_ZR || ((p.Cout_g >> 1) % 16 == 0)))
                      ? 1 : 0;
   }
-  if (pp_prog_recording()) return pp_prog_record_conv(p);
-  if (pp_conv_halo_eligible(p)) return pp_launch_conv_halo(p, stream);
+  if (pp_prog_recording()) { g_last_kind = 'p'; return pp_prog_record_conv(p); }
+  if (pp_conv_halo_eligible(p)) { g_last_kind = 'h'; return pp_launch_conv_halo(p, stream); }
+  g_last_kind = 'i';
   PP_REQUIRE(!p.ups2x, "conv: fused x2 upsampling needs the TMA halo kernel (stride 1, one input segment, even H and W)");
   for (int i = 0; i < p.nseg; ++i)
     PP_REQUIRE(p.seg[i].cvalid == 0, "conv: zero-extended input channels (cvalid=%d of %d) need the TMA halo kernel "

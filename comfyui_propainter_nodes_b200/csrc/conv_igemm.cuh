@@ -58,6 +58,9 @@ struct PPConvParams {
 };
 
 int pp_launch_conv(const PPConvParams& p, cudaStream_t stream);
+// which kernel the last pp_launch_conv of this thread went to: 'h' TMA halo-tile kernel, 'i' cp.async implicit GEMM,
+// 'p' recorded into a multi-layer program (profiling labels)
+char pp_last_conv_kind();
 // conv_halo.cu: TMA halo-tile kernel for stride-1 convolutions (dispatched from pp_launch_conv when eligible;
 // PP_CONV_HALO=0 in the environment disables it).  `p` must already carry num_kc / vec_ok.
 int pp_conv_halo_eligible(const PPConvParams& p);

@@ -131,5 +131,8 @@ int PPConvCall::run(cudaStream_t st) {
     if (it != eng->convs.end() && it->second.macs_per_pixel > 0.0) macs = it->second.macs_per_pixel;
   }
   PPProfScope ps(*eng, "conv:" + name, rows, 2.0 * rows * macs, 0.0, st);
-  return pp_launch_conv(p, st);
+  const int rc = pp_launch_conv(p, st);
+  if (eng->profile && !eng->prof.empty())      // label the record with the kernel the launch was dispatched to
+    eng->prof.back().name = std::string(pp_last_conv_kind() == 'h' ? "conv:halo:" : "conv:igemm:") + name;
+  return rc;
 }

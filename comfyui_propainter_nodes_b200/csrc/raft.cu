@@ -187,7 +187,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
         p.out = corr[0] + (size_t)sb.off * P * P; p.out_cstride = P; p.out_coff = 0; p.out_fp32 = 0;
         p.out_gstep = P * P;
         {
-          PPProfScope ps(e, "conv:raft.corr", (double)Ms, 2.0 * Ms * P * 256, (double)Ms * P * 2 + 2.0 * Ms * 256 * 2, st);
+          PPProfScope ps(e, "conv:igemm:raft.corr", (double)Ms, 2.0 * Ms * P * 256, (double)Ms * P * 2 + 2.0 * Ms * 256 * 2, st);
           PP_TRY(pp_launch_conv(p, st));
         }
         e.launches++;

@@ -188,7 +188,7 @@ int pp_stage_flow_complete(PPEngine& e, const float* flows_f, const float* flows
         PP_TRY(PPConvCall(e, m + ".backbone.1", D, h8, w8).in(bb, 128, 0, 128).out(feats + (size_t)idx * slice, 128, 0)
                    .residual(prop, 128, 0).run(st));
         if (prog) {
-          PPProfScope ps(e, "conv:rfc.fp.step_program", (double)D * P, e.prog_flops, 0.0, st);
+          PPProfScope ps(e, "conv:prog:rfc.fp.step", (double)D * P, e.prog_flops, 0.0, st);
           pg.armed = false;
           PP_TRY(pp_prog_end(e.prog_counter, &e.prog_arrivals, st));
           e.launches++;
