@@ -89,20 +89,13 @@ __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (
 // Epilogue operands that do not depend on the accumulator (residual / GRU h and z), fetched while the TMEM read of
 // the same 16 columns is still in flight so the two latencies overlap instead of adding up.
 struct EpiAux {
-  uint4 a0[2], a1[2], a2[2];
-  bool have, have2;
+  uint4 a0[2], a1[2];
+  bool have;
 };
 __device__ __forceinline__ void conv_epilogue_prefetch16(const PPConvParams& p, long long mrow, int ng0, int epi, bool vec,
                                                          EpiAux& x) {
   x.have = false;
-  x.have2 = false;
   if (!vec || p.Cout_g - ng0 < 16) return;
-  if (p.pre != nullptr && epi != PP_EPI_STD) {     // pre-activation addend of the GRU gates: all 16 columns, every tile
-    const __half* s2 = p.pre + mrow * p.pre_cstride + p.pre_coff + ng0;
-    x.have2 = true;
-    if (p.vec32_ok) ldg256(s2, x.a2[0], x.a2[1]);
-    else { x.a2[0] = reinterpret_cast<const uint4*>(s2)[0]; x.a2[1] = reinterpret_cast<const uint4*>(s2)[1]; }
-  }
   const __half* s0 = nullptr;
   const __half* s1 = nullptr;
   if (epi == PP_EPI_STD) {
@@ -183,13 +176,6 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
       }
     } else if (epi == PP_EPI_GRU_ZR) {
       const int half_c = p.Cout_g >> 1;
-      if (p.pre != nullptr) {
-        float c[16];
-        if (pre != nullptr && pre->have2) unpack16(pre->a2[0], pre->a2[1], c);
-        else load16(p.pre + mrow * p.pre_cstride + p.pre_coff + ng0, nvalid, vec, c);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += c[i];
-      }
       act16_t<PP_ACT_SIGMOID>(v, 0.f);
       if (ng0 < half_c) {
         store16(reinterpret_cast<__half*>(p.out) + mrow * p.out_cstride + p.out_coff + ng0, nvalid, vec, v, v32);
@@ -210,13 +196,6 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
       } else {
         load16(p.aux0 + mrow * p.aux0_cstride + p.aux0_coff + ng0, nvalid, vec, h);
         load16(p.aux1 + mrow * p.aux1_cstride + p.aux1_coff + ng0, nvalid, vec, z);
-      }
-      if (p.pre != nullptr) {
-        float c[16];
-        if (pre != nullptr && pre->have2) unpack16(pre->a2[0], pre->a2[1], c);
-        else load16(p.pre + mrow * p.pre_cstride + p.pre_coff + ng0, nvalid, vec, c);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += c[i];
       }
       act16_t<PP_ACT_TANH>(v, 0.f);
 #pragma unroll

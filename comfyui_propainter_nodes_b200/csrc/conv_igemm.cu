@@ -266,8 +266,7 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
       return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && cs % per == 0 && co % per == 0 && gs % per == 0);
     };
     bool ok = al(p.out, p.out_cstride, p.out_coff, p.out_gstep, per16) && al(p.aux0, p.aux0_cstride, p.aux0_coff, 0, 8) &&
-              al(p.aux1, p.aux1_cstride, p.aux1_coff, 0, 8) && al(p.out2, p.out2_cstride, p.out2_coff, 0, 8) &&
-              al(p.pre, p.pre_cstride, p.pre_coff, 0, 8);
+              al(p.aux1, p.aux1_cstride, p.aux1_coff, 0, 8) && al(p.out2, p.out2_cstride, p.out2_coff, 0, 8);
     if (p.bias != nullptr) ok = ok && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && (p.groups == 1 || p.Cout_g % 4 == 0);
     if (p.epi == PP_EPI_GRU_ZR) ok = ok && ((p.Cout_g >> 1) % 16 == 0);
     p.vec_ok = ok ? 1 : 0;
@@ -276,7 +275,7 @@ int pp_launch_conv(const PPConvParams& pin, cudaStream_t stream) {
     };
     p.vec32_ok = (ok && !p.out_fp32 && al32(p.out, p.out_cstride, p.out_coff, p.out_gstep) &&
                   al32(p.aux0, p.aux0_cstride, p.aux0_coff, 0) && al32(p.aux1, p.aux1_cstride, p.aux1_coff, 0) &&
-                  al32(p.out2, p.out2_cstride, p.out2_coff, 0) && al32(p.pre, p.pre_cstride, p.pre_coff, 0) && (p.epi != PP_EPI_GRU_ZR || ((p.Cout_g >> 1) % 16 == 0)))
+                  al32(p.out2, p.out2_cstride, p.out2_coff, 0) && (p.epi != PP_EPI_GRU_ZR || ((p.Cout_g >> 1) % 16 == 0)))
                      ? 1 : 0;
   }
   if (pp_prog_recording()) { g_last_kind = 'p'; return pp_prog_record_conv(p); }

@@ -53,8 +53,6 @@ struct PPConvParams {
   const __half* aux0; int aux0_cstride, aux0_coff;   // residual (STD) or h (GRU)
   const __half* aux1; int aux1_cstride, aux1_coff;   // z (GRU_H)
   __half* out2; int out2_cstride, out2_coff;          // r*h destination (GRU_ZR)
-  const __half* pre; int pre_cstride, pre_coff;       // GRU epilogues: added to the accumulator BEFORE the gate non-linearity
-                                                      // (the iteration-invariant context part of the gate conv, computed once)
 };
 
 int pp_launch_conv(const PPConvParams& p, cudaStream_t stream);

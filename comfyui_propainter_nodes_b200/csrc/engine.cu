@@ -96,11 +96,6 @@ PPConvCall& PPConvCall::gru_h(const __half* h, int h_cs, int h_co, const __half*
   return *this;
 }
 
-PPConvCall& PPConvCall::pre(const __half* ptr, int cs, int co) {
-  p.pre = ptr; p.pre_cstride = cs; p.pre_coff = co;
-  return *this;
-}
-
 int PPConvCall::run(cudaStream_t st) {
   if (err != PP_OK) return err;
   if (p.nseg > 0 && p.seg[p.nseg - 1].cend < p.Cin && p.Cin % 64 == 0 && p.Cin - p.seg[p.nseg - 1].cend < 64 &&

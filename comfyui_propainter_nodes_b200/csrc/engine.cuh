@@ -123,7 +123,6 @@ struct PPConvCall {
   PPConvCall& residual(const __half* ptr, int cs, int co);
   PPConvCall& gru_zr(const __half* h, int h_cs, int h_co, __half* rh, int rh_cs, int rh_co);
   PPConvCall& gru_h(const __half* h, int h_cs, int h_co, const __half* z, int z_cs, int z_co);
-  PPConvCall& pre(const __half* ptr, int cs, int co);   // GRU epilogues: pre-activation addend (context part of the gate conv)
   int run(cudaStream_t st);
 };
 

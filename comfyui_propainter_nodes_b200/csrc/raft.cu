@@ -138,7 +138,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
   const int lvl_h[4] = {h8, h8 >> 1, h8 >> 2, h8 >> 3}, lvl_w[4] = {w8, w8 >> 1, w8 >> 2, w8 >> 3};
   size_t corr_elems = 0;
   for (int l = 0; l < 4; ++l) corr_elems += (size_t)P * lvl_h[l] * lvl_w[l];
-  const size_t per_pair = corr_elems * 2 + (size_t)P * (384 + 128 + 128 + 328 + 256 + 256 + 128 + 8 + 256 + 768) * 2 +
+  const size_t per_pair = corr_elems * 2 + (size_t)P * (384 + 128 + 128 + 328 + 256 + 256 + 128 + 8 + 256) * 2 +
                           (size_t)P * 4 * 4 + (size_t)P * 32 * 4 + (size_t)P * 576 * 2;
   const size_t avail = e.arena.cap - e.arena.off;
   int max_pairs = (int)(avail * 9 / 10 / per_pair);
@@ -208,9 +208,6 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
       PP_TRY(pp_alloc(e, &f1b, (size_t)M * 128, "f1"));
       PP_TRY(pp_alloc(e, &flow8, (size_t)M * 8, "flow8"));
       PP_TRY(pp_alloc(e, &fh, (size_t)M * 256, "flow head"));
-      // iteration-invariant context part of the four GRU gate convs (z|r and q of the horizontal and the vertical GRU)
-      __half* ctx;
-      PP_TRY(pp_alloc(e, &ctx, (size_t)M * 768, "gru context terms"));
       PP_TRY(pp_alloc(e, &coords1, (size_t)M * 2, "coords1"));
       PP_TRY(pp_alloc(e, &delta, (size_t)M * 2, "delta"));
       for (int si = 0; si < nsub; ++si) {
@@ -221,13 +218,6 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
       }
       PP_TRY(pp_k_raft_coords_init(coords1, flow8, hx, 384, 382, B, h8, w8, st));
       e.launches++;
-      // W_gate[:, inp] * inp, once per batch: ctx = [zr1 (256) | q1 (128) | zr2 (256) | q2 (128)] per pixel, no bias
-      {
-        const int off[4] = {0, 256, 384, 640};
-        const char* nm[4] = {"raft.update.gru.zr1.ctx", "raft.update.gru.q1.ctx", "raft.update.gru.zr2.ctx", "raft.update.gru.q2.ctx"};
-        for (int k = 0; k < 4; ++k)
-          PP_TRY(PPConvCall(e, nm[k], B, h8, w8).in(hx, 384, 128, 128).out(ctx, 768, off[k]).run(st));
-      }
 
       for (int it = 0; it < iters; ++it) {
         {
@@ -250,11 +240,10 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
         // SepConvGRU (update.py:35-73): horizontal (1x5) then vertical (5x1)
         for (int half = 1; half <= 2; ++half) {
           const std::string s = std::to_string(half);
-          const int cz = half == 1 ? 0 : 384, cq = half == 1 ? 256 : 640;     // this GRU's context terms
-          PP_TRY(PPConvCall(e, "raft.update.gru.zr" + s, B, h8, w8).in(hx, 384, 0, 128).in(hx, 384, 256, 128).out(z, 128, 0)
-                     .gru_zr(hx, 384, 0, rh, 128, 0).pre(ctx, 768, cz).run(st));
-          PP_TRY(PPConvCall(e, "raft.update.gru.q" + s, B, h8, w8).in(rh, 128, 0, 128).in(hx, 384, 256, 128)
-                     .out(hx, 384, 0).gru_h(hx, 384, 0, z, 128, 0).pre(ctx, 768, cq).run(st));
+          PP_TRY(PPConvCall(e, "raft.update.gru.zr" + s, B, h8, w8).in(hx, 384, 0, 384).out(z, 128, 0)
+                     .gru_zr(hx, 384, 0, rh, 128, 0).run(st));
+          PP_TRY(PPConvCall(e, "raft.update.gru.q" + s, B, h8, w8).in(rh, 128, 0, 128).in(hx, 384, 128, 256)
+                     .out(hx, 384, 0).gru_h(hx, 384, 0, z, 128, 0).run(st));
         }
         // FlowHead (update.py:6-14)
         PP_TRY(PPConvCall(e, "raft.update.fh1", B, h8, w8).in(hx, 384, 0, 128).out(fh, 256, 0)

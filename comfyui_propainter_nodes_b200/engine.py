@@ -183,20 +183,10 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
     add("raft.update.convf1", r[u + "encoder.convf1.weight"], r[u + "encoder.convf1.bias"], 1, _pad_map(2, 8))
     add("raft.update.convf2", r[u + "encoder.convf2.weight"], r[u + "encoder.convf2.bias"])
     add("raft.update.conv", r[u + "encoder.conv.weight"], r[u + "encoder.conv.bias"])
-    # SepConvGRU gates (update.py:35-73) convolve cat(h, x) with x = cat(inp, motion): the context `inp` does not change
-    # over the GRU iterations, so its part of every gate conv is computed ONCE per clip ("ctx" weights, input channels
-    # 128..255, no bias) and added before the gate non-linearity; the per-iteration convs ("dyn") see only h / r*h and the
-    # motion features (input channels 0..127 and 256..383): a third less work in the four largest layers of the loop.
-    dyn_map, ctx_map = list(range(0, 128)) + list(range(256, 384)), list(range(128, 256))
     for s in ("1", "2"):
-        wzr = torch.cat([r[u + f"gru.convz{s}.weight"], r[u + f"gru.convr{s}.weight"]], 0)
-        bzr = torch.cat([r[u + f"gru.convz{s}.bias"], r[u + f"gru.convr{s}.bias"]], 0)
-        wq, bq = r[u + f"gru.convq{s}.weight"], r[u + f"gru.convq{s}.bias"]
-        taps = wzr.shape[2] * wzr.shape[3]
-        add("raft.update.gru.zr" + s, wzr, bzr, 1, dyn_map, macs=wzr.shape[0] * 256 * taps)
-        add("raft.update.gru.q" + s, wq, bq, 1, dyn_map, macs=wq.shape[0] * 256 * taps)
-        add("raft.update.gru.zr" + s + ".ctx", wzr, None, 1, ctx_map, macs=wzr.shape[0] * 128 * taps)
-        add("raft.update.gru.q" + s + ".ctx", wq, None, 1, ctx_map, macs=wq.shape[0] * 128 * taps)
+        add("raft.update.gru.zr" + s, torch.cat([r[u + f"gru.convz{s}.weight"], r[u + f"gru.convr{s}.weight"]], 0),
+            torch.cat([r[u + f"gru.convz{s}.bias"], r[u + f"gru.convr{s}.bias"]], 0))
+        add("raft.update.gru.q" + s, r[u + f"gru.convq{s}.weight"], r[u + f"gru.convq{s}.bias"])
     add("raft.update.fh1", r[u + "flow_head.conv1.weight"], r[u + "flow_head.conv1.bias"])
     add("raft.update.fh2", r[u + "flow_head.conv2.weight"], r[u + "flow_head.conv2.bias"])
     add("raft.update.mask0", r[u + "mask.0.weight"], r[u + "mask.0.bias"])
