@@ -124,8 +124,11 @@ __device__ __forceinline__ void conv_epilogue_prefetch16(const PPConvParams& p, 
 
 // `raw`: 16 fp32 accumulators (TMEM columns ng0-n0 .. +15) of output pixel `mrow` (flattened N*OH*OW index),
 // group g, first channel ng0 (within the group; ng0 < Cout_g).  `epi`/`vec` are launch-uniform.
+// sm0 / sm1 (STD epilogue, fp16 output only): when non-null the 16 results go to these two 16-byte shared-memory slots
+// (a staging tile that a TMA store writes out) instead of global memory.
 __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uint32_t (&raw)[16], long long mrow, int g,
-                                                int ng0, int epi, bool vec, const EpiAux* pre = nullptr) {
+                                                int ng0, int epi, bool vec, const EpiAux* pre = nullptr,
+                                                uint4* sm0 = nullptr, uint4* sm1 = nullptr) {
     const int nvalid = min(16, p.Cout_g - ng0);
     const bool v32 = p.vec32_ok != 0;
     float v[16];
@@ -171,6 +174,12 @@ __device__ __forceinline__ void conv_epilogue16(const PPConvParams& p, const uin
           for (int i = 0; i < 16; ++i)
             if (i < nvalid) dst[i] = v[i];
         }
+      } else if (sm0 != nullptr) {
+        __align__(16) __half2 h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        *sm0 = reinterpret_cast<uint4*>(h)[0];
+        *sm1 = reinterpret_cast<uint4*>(h)[1];
       } else {
         store16(reinterpret_cast<__half*>(p.out) + o, nvalid, vec, v, v32);
       }

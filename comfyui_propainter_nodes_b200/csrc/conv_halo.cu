@@ -58,6 +58,12 @@ struct HaloParams {
   int LBW, LBH;      // low-res staging box (pixels)
   int l_stage_bytes;
   int debug;         // bit 0: skip the epilogue math/stores (PP_CONV_NOEPI=1, mainloop-only timing experiments)
+  // flat-mode layers with few K chunks are bound by the epilogue's per-thread 32-byte global stores (one L1 wavefront per
+  // lane).  tstore: the epilogue writes the fp16 tile into a 128B-swizzled shared-memory staging tile and ONE thread
+  // issues TMA stores ([128 rows x 64 columns] boxes, rows / columns beyond the tensor clipped by the TMA unit).
+  int tstore;
+  int out_stage_bytes;     // staging bytes per sub-tile: ceil(BN / 64) panels of [128 rows][128 B]
+  CUtensorMap tmap_out;
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -65,6 +71,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
       "l"(tmap), "r"(ppx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
 }
 
 struct TileCoord {
@@ -98,6 +109,7 @@ __global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_
   uint64_t* l_full = acc_empty + 2;     // UPS: low-res staging ring (2 stages)
   uint64_t* l_empty = l_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_empty + 2);
+  uint8_t* stg_out = smem_b + h.SB * h.b_stage_bytes + 2048;     // TMA-store staging (flat layers), 1024-byte aligned
   constexpr int W_B = UPS ? UPS_WARP_B : WARP_B, W_MMA = UPS ? UPS_WARP_MMA : WARP_MMA;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -161,6 +173,15 @@ __global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_
       tc_fence_after();
       const uint32_t t_row = tmem_base + lane_base + set * set_cols + sub * h.accw;
       const bool skip = !mvalid || (h.debug & 1);
+      // TMA-store path: staging tile of this sub-tile, its barrier (the 4 warps of a sub-tile, or all 8 when MT == 1)
+      uint8_t* stg = nullptr;
+      const int bar_id = 2 + (h.MT == 2 ? half : 0), bar_n = h.MT == 2 ? 128 : 256;
+      const bool issuer = h.MT == 2 ? (tid == half * 128) : (tid == 0);
+      if (h.tstore) {
+        stg = stg_out + sub * h.out_stage_bytes;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's stores have read it
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
+      }
       // 32 columns per round: both TMEM loads are in flight before the single wait
       for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t raw0[16], raw1[16];
@@ -179,14 +200,35 @@ __global__ void __launch_bounds__(UPS ? UPS_THREADS : NUM_THREADS, 1) conv_halo_
           tc_fence_before();
           mbar_arrive(&acc_empty[set]);
         }
-        if (do0) ppconv::conv_epilogue16(p, raw0, mrow, t.g, n0 + c0, epi, vec, &x0);
-        if (do1) ppconv::conv_epilogue16(p, raw1, mrow, t.g, n0 + c0 + 16, epi, vec, &x1);
+        if (stg != nullptr) {
+          // 16 columns = two 16-byte units of panel c/64, row r, 128B swizzle (unit index XOR row & 7)
+          auto slot = [&](int c, int u) {
+            const int unit = ((c & 63) >> 3) + u;
+            return reinterpret_cast<uint4*>(stg + (c >> 6) * 16384 + r * 128 + ((unit ^ (r & 7)) << 4));
+          };
+          if (do0) ppconv::conv_epilogue16(p, raw0, mrow, t.g, n0 + c0, epi, vec, &x0, slot(c0, 0), slot(c0, 1));
+          if (do1) ppconv::conv_epilogue16(p, raw1, mrow, t.g, n0 + c0 + 16, epi, vec, &x1, slot(c0 + 16, 0), slot(c0 + 16, 1));
+        } else {
+          if (do0) ppconv::conv_epilogue16(p, raw0, mrow, t.g, n0 + c0, epi, vec, &x0);
+          if (do1) ppconv::conv_epilogue16(p, raw1, mrow, t.g, n0 + c0 + 16, epi, vec, &x1);
+        }
       }
       if (c_lo >= c_hi) {
         tc_fence_before();
         mbar_arrive(&acc_empty[set]);
       }
+      if (stg != nullptr) {
+        fence_proxy_async();                                  // generic-proxy smem writes -> visible to the TMA store
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_n) : "memory");
+        if (issuer && !(h.debug & 1)) {
+          const int row0 = (int)(((long long)t.tx * h.MT + sub) * 128);
+          for (int pnl = 0; pnl * 64 < bnt; ++pnl)
+            tma_store_2d(&h.tmap_out, smem_u32(stg + pnl * 16384), n0 + pnl * 64, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
+    if (h.tstore) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // outstanding stores of this thread complete
   } else if (UPS && warp < 12) {
     // ------------------------------------------------------------------ fused bilinear x2 (align_corners=True) producer
     // The conv's input is the x2 upsampling of a half-resolution tensor (reference deconv = F.interpolate + conv).
@@ -847,16 +889,50 @@ int halo_configure(const PPConvParams& pin, HaloParams& h, bool one_wave) {
   h.LH = p.H / 2; h.LW = p.W / 2;
   h.LBW = (h.BW - 1) / 2 + 3; h.LBH = (h.BH - 1) / 2 + 3;      // low-res pixels that can feed BW x BH hi-res ones
   h.l_stage_bytes = h.ups ? pp_ceil_div(h.LBW * h.LBH * 128, 1024) * 1024 : 0;
-  const int budget = SMEM_BUDGET - 2 * h.l_stage_bytes - (h.ups ? 1024 : 0);
+  // TMA-store epilogue (see HaloParams::tstore): flat layers with few K chunks, plain fp16 output
+  h.tstore = 0;
+  h.out_stage_bytes = 0;
+  {
+    static int ts_on = -1;
+    if (ts_on < 0) { const char* e = getenv("PP_TMA_STORE"); ts_on = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+    if (ts_on && !one_wave && flat && !h.ups && p.epi == PP_EPI_STD && !p.out_fp32 && p.groups == 1 && p.out_gstep == 0 &&
+        bn % 64 == 0 && p.vec_ok && h.chunks <= 16 && p.out_cstride % 8 == 0 && p.out_coff % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+      h.tstore = 1;
+      h.out_stage_bytes = (bn / 64) * 16384;
+    }
+  }
+  const int budget = SMEM_BUDGET - 2 * h.l_stage_bytes - (h.ups ? 1024 : 0) - (h.tstore ? mt * h.out_stage_bytes + 1024 : 0);
   int sa = h.ups ? 2 : 3, sb = 0;
   for (; sa >= 2; --sa) {
     sb = (budget - sa * h.a_stage_bytes) / h.b_stage_bytes;
     if (sb >= 3) break;
   }
+  if (h.tstore && !(sa >= 2 && sb >= 3)) {      // no room for the staging tile: plain epilogue
+    h.tstore = 0;
+    h.out_stage_bytes = 0;
+    const int budget2 = SMEM_BUDGET - 2 * h.l_stage_bytes - (h.ups ? 1024 : 0);
+    for (sa = 3; sa >= 2; --sa) {
+      sb = (budget2 - sa * h.a_stage_bytes) / h.b_stage_bytes;
+      if (sb >= 3) break;
+    }
+  }
   PP_REQUIRE(sa >= 2 && sb >= 3, "conv_halo: patch %dx%d does not fit shared memory", h.BW, h.BH);
   if (sb > MAX_SB) sb = MAX_SB;
   if (!h.ups && sa == 3 && sb == MAX_SB && (budget - 4 * h.a_stage_bytes) / h.b_stage_bytes >= MAX_SB) sa = 4;
   h.SA = sa; h.SB = sb;
+  if (h.tstore) {
+    cuuint64_t dims[2] = {(cuuint64_t)p.Cout_g, (cuuint64_t)p.M_total};
+    cuuint64_t strides[1] = {(cuuint64_t)p.out_cstride * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t es[2] = {1, 1};
+    EncodeTiledFn enc_o = encode_fn();
+    PP_REQUIRE(enc_o != nullptr, "conv_halo: cuTensorMapEncodeTiled is not available");
+    const CUresult r = enc_o(&h.tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, reinterpret_cast<__half*>(p.out) + p.out_coff, dims,
+                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PP_REQUIRE(r == CUDA_SUCCESS, "conv_halo: cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+  }
   { const char* e = getenv("PP_CONV_NOEPI"); h.debug = (e != nullptr && atoi(e) != 0) ? 1 : 0; }
   const long long total_tiles = count(mt, bn);
   PP_REQUIRE(total_tiles < (1LL << 31), "conv_halo: too many tiles");
@@ -901,7 +977,7 @@ int pp_launch_conv_halo(const PPConvParams& pin, cudaStream_t stream) {
   PP_TRY(halo_num_sms(&num_sms));
   const long long total_tiles = halo_total_tiles(h);
   const size_t smem = (size_t)h.SA * h.a_stage_bytes + (size_t)h.SB * h.b_stage_bytes + 1024 + 512 + 2 * (size_t)h.l_stage_bytes +
-                      (h.ups ? 1024 : 0);
+                      (h.ups ? 1024 : 0) + (h.tstore ? (size_t)h.MT * h.out_stage_bytes + 1536 : 0);
   const int grid = (int)(total_tiles < num_sms ? total_tiles : num_sms);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
