@@ -33,6 +33,7 @@ int pp_k_raft_coords_init(float* coords1, __half* flow8, __half* hx, int hx_cs, 
                           cudaStream_t st);
 int pp_k_raft_coords_update(const float* delta, float* coords1, __half* flow8, __half* hx, int hx_cs, int hx_flow_co,
                             int B, int h8, int w8, cudaStream_t st);
+int pp_k_flow_patch7x7(const __half* flow8, __half* out /*[M][128]*/, int B, int h8, int w8, cudaStream_t st);
 int pp_k_convex_upsample(const float* coords1, const __half* mask, float* out_nchw, int B, int h8, int w8,
                          cudaStream_t st);
 

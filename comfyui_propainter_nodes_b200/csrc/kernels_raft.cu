@@ -338,6 +338,40 @@ int pp_k_cnet_split(const __half* c, __half* hx, int hx_cs, long long npix, cuda
   return PP_OK;
 }
 
+// im2col of the 2-channel flow for BasicMotionEncoder.convf1 (7x7, pad 3; update.py:97,105): per pixel the 49 taps x (dx, dy)
+// = 98 values in (ky, kx, channel) order, zero outside the map, zero-padded to 128 -> [M][128] fp16, so that the layer runs
+// as a K = 128 flat GEMM on the TMA kernel instead of a K = 49 x 8 (6 of 8 channels padding) implicit GEMM.
+// One thread per (pixel, 16-byte unit = 4 taps).
+__global__ void flow_patch7x7(const __half* __restrict__ flow8, uint4* __restrict__ out, int h, int w, long long total_units) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total_units) return;
+  const int u = (int)(idx & 15);
+  const long long pix = idx >> 4;
+  const int hw = h * w;
+  const long long img = pix / hw;
+  const int p = (int)(pix - img * hw), y = p / w, x = p - y * w;
+  __align__(16) __half2 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int tap = u * 4 + i;
+    v[i] = __floats2half2_rn(0.f, 0.f);
+    if (tap < 49) {
+      const int yy = y + tap / 7 - 3, xx = x + tap % 7 - 3;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+        v[i] = *reinterpret_cast<const __half2*>(flow8 + ((img * hw + (long long)yy * w + xx) << 3));
+    }
+  }
+  out[idx] = *reinterpret_cast<uint4*>(v);
+}
+
+int pp_k_flow_patch7x7(const __half* flow8, __half* out, int B, int h8, int w8, cudaStream_t st) {
+  const long long total = (long long)B * h8 * w8 * 16;
+  if (total == 0) return PP_OK;
+  flow_patch7x7<<<nblocks(total), TPB, 0, st>>>(flow8, reinterpret_cast<uint4*>(out), h8, w8, total);
+  PP_CUDA_CHECK(cudaGetLastError());
+  return PP_OK;
+}
+
 int pp_k_raft_coords_init(float* coords1, __half* flow8, __half* hx, int hx_cs, int hx_flow_co, int B, int h8, int w8,
                           cudaStream_t st) {
   const long long total = (long long)B * h8 * w8;

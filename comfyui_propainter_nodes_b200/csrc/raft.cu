@@ -138,7 +138,7 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
   const int lvl_h[4] = {h8, h8 >> 1, h8 >> 2, h8 >> 3}, lvl_w[4] = {w8, w8 >> 1, w8 >> 2, w8 >> 3};
   size_t corr_elems = 0;
   for (int l = 0; l < 4; ++l) corr_elems += (size_t)P * lvl_h[l] * lvl_w[l];
-  const size_t per_pair = corr_elems * 2 + (size_t)P * (384 + 128 + 128 + 328 + 256 + 256 + 128 + 8 + 256) * 2 +
+  const size_t per_pair = corr_elems * 2 + (size_t)P * (384 + 128 + 128 + 328 + 256 + 256 + 128 + 128 + 8 + 256) * 2 +
                           (size_t)P * 4 * 4 + (size_t)P * 32 * 4 + (size_t)P * 576 * 2;
   const size_t avail = e.arena.cap - e.arena.off;
   int max_pairs = (int)(avail * 9 / 10 / per_pair);
@@ -206,6 +206,8 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
       PP_TRY(pp_alloc(e, &c1, (size_t)M * 256, "c1"));
       PP_TRY(pp_alloc(e, &corflo, (size_t)M * 256, "corflo"));
       PP_TRY(pp_alloc(e, &f1b, (size_t)M * 128, "f1"));
+      __half* fpatch;
+      PP_TRY(pp_alloc(e, &fpatch, (size_t)M * 128, "flow patches"));
       PP_TRY(pp_alloc(e, &flow8, (size_t)M * 8, "flow8"));
       PP_TRY(pp_alloc(e, &fh, (size_t)M * 256, "flow head"));
       PP_TRY(pp_alloc(e, &coords1, (size_t)M * 2, "coords1"));
@@ -231,7 +233,10 @@ int pp_stage_raft(PPEngine& e, const float* frames, int T, int H, int W, int ite
                    .out(c1, 256, 0).act(PP_ACT_RELU).run(st));
         PP_TRY(PPConvCall(e, "raft.update.convc2", B, h8, w8).in(c1, 256, 0, 256).out(corflo, 256, 0)
                    .act(PP_ACT_RELU).run(st));
-        PP_TRY(PPConvCall(e, "raft.update.convf1", B, h8, w8).in(flow8, 8, 0, 8).out(f1b, 128, 0)
+        // convf1 (7x7 over the 2-channel flow): explicit 98-wide patches + a K = 128 linear layer
+        PP_TRY(pp_k_flow_patch7x7(flow8, fpatch, B, h8, w8, st));
+        e.launches++;
+        PP_TRY(PPConvCall(e, "raft.update.convf1", 1, 1, (int)M).in(fpatch, 128, 0, 128).geom(1, 1, 0, 0).out(f1b, 128, 0)
                    .act(PP_ACT_RELU).run(st));
         PP_TRY(PPConvCall(e, "raft.update.convf2", B, h8, w8).in(f1b, 128, 0, 128).out(corflo, 256, 192)
                    .act(PP_ACT_RELU).run(st));

@@ -180,7 +180,11 @@ def build_layers(raft_sd, rfc_sd, gen_sd):
     u = "update_block."
     add("raft.update.convc1", r[u + "encoder.convc1.weight"], r[u + "encoder.convc1.bias"], 1, _pad_map(324, 328))
     add("raft.update.convc2", r[u + "encoder.convc2.weight"], r[u + "encoder.convc2.bias"])
-    add("raft.update.convf1", r[u + "encoder.convf1.weight"], r[u + "encoder.convf1.bias"], 1, _pad_map(2, 8))
+    # convf1 (7x7 over the 2-channel flow) as a linear layer over explicit 7x7x2 patches in (ky, kx, channel) order,
+    # zero-padded 98 -> 128 (kernels_raft.cu: flow_patch7x7)
+    wf1 = r[u + "encoder.convf1.weight"]                                   # [128, 2, 7, 7]
+    wf1 = torch.cat([wf1.permute(0, 2, 3, 1).reshape(128, 98), torch.zeros(128, 30)], 1).view(128, 128, 1, 1)
+    add("raft.update.convf1", wf1, r[u + "encoder.convf1.bias"], 1, None, macs=128 * 98)
     add("raft.update.convf2", r[u + "encoder.convf2.weight"], r[u + "encoder.convf2.bias"])
     add("raft.update.conv", r[u + "encoder.conv.weight"], r[u + "encoder.conv.bias"])
     for s in ("1", "2"):
