@@ -349,9 +349,11 @@ def run_b200(args, rank, world):
     node = ProPainterInpaint()
 
     def e2e_step():
-        if strong:   # host tensors -> device pre-processing -> sharded clip -> float IMAGE back on the host
+        if strong:   # host tensors -> device pre-processing on every rank -> sharded clip -> float IMAGE back on the
+            # host of rank 0 (the caller's process); the other ranks hold the same result in HBM and return it there
             f, m1, m2, o = eng.preprocess(image, mask, PARAMS["flow_mask_dilates"], PARAMS["mask_dilates"])
-            return _to_host(eng.postprocess(PAR.inpaint_clip_distributed(models, f, m1, m2, o, cfg)))
+            out = eng.postprocess(PAR.inpaint_clip_distributed(models, f, m1, m2, o, cfg))
+            return _to_host(out) if rank == 0 else out
         with contextlib.redirect_stdout(sys.stderr):   # the node prints progress; stdout carries only the JSON line
             frames, _, _ = node.propainter_inpainting(image, mask, WIDTH, HEIGHT, **PARAMS)
         return frames
