@@ -216,3 +216,33 @@ def test_bench_reference_arm_prints_one_json_line(monkeypatch, capfd):
     assert rec["impl"] == "reference" and rec["cpu_baseline"]["kind"] == "port" and rec["e2e"]["h2d_bytes_per_step"] == 0
     bench.run_reference(args, rank=1)            # other ranks stay silent
     assert capfd.readouterr().out == ""
+
+
+def test_pil_bicubic_restatement_matches_pillow():
+    """oracle/pil_resize.py (the arithmetic the device resize kernel implements) == Pillow's Image.resize, bit for bit."""
+    from PIL import Image
+    from oracle import pil_resize as PR
+    rng = np.random.RandomState(0)
+    for (H, W, oh, ow) in ((180, 320, 176, 320), (64, 96, 48, 72), (50, 70, 120, 200), (97, 131, 40, 57), (36, 64, 48, 64)):
+        img = rng.randint(0, 256, (H, W, 3), dtype=np.uint8)
+        assert np.array_equal(PR.resize_u8(img, ow, oh), np.array(Image.fromarray(img).resize((ow, oh)))), (H, W, oh, ow)
+        m = rng.randint(0, 256, (H, W), dtype=np.uint8)
+        assert np.array_equal(PR.resize_u8(m, ow, oh), np.array(Image.fromarray(m).resize((ow, oh)))), (H, W, oh, ow)
+
+
+def test_host_quantiser_matches_reference_conversion():
+    """pp_host_quantize_u8 (host helper of the e2e path, no GPU) == (x * 255).clip(0, 255).astype(uint8) of the reference
+    (utils/image_utils.py:106-114), incl. out-of-range values, for every thread count."""
+    lib = E.load_library()
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(3, 40, 56, 3, generator=g) * 1.4 - 0.2
+    x[0, 0, 0, :] = torch.tensor([1.0, 0.0, 0.999999])
+    ref = (x.numpy() * 255.0).clip(0, 255).astype(np.uint8)
+    for threads in (1, 3, 16):
+        out = torch.empty(x.shape, dtype=torch.uint8)
+        assert lib.pp_host_quantize_u8(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), x.numel(), threads) == 0
+        assert np.array_equal(out.numpy(), ref), threads
+    big = torch.rand(1 << 18, generator=g)
+    out = torch.empty(big.shape, dtype=torch.uint8)
+    assert lib.pp_host_quantize_u8(ctypes.c_void_p(big.data_ptr()), ctypes.c_void_p(out.data_ptr()), big.numel(), 8) == 0
+    assert np.array_equal(out.numpy(), (big.numpy() * 255.0).clip(0, 255).astype(np.uint8))
