@@ -246,3 +246,23 @@ def test_host_quantiser_matches_reference_conversion():
     out = torch.empty(big.shape, dtype=torch.uint8)
     assert lib.pp_host_quantize_u8(ctypes.c_void_p(big.data_ptr()), ctypes.c_void_p(out.data_ptr()), big.numel(), 8) == 0
     assert np.array_equal(out.numpy(), (big.numpy() * 255.0).clip(0, 255).astype(np.uint8))
+
+
+def test_window_sub_batches_cover_the_schedule_in_order():
+    """Engine.gen_batches (host logic of the small-workspace fallback): consecutive sub-batches, nothing dropped or
+    reordered, every batch within the budget unless it is a single window."""
+    from oracle import propainter_oracle as O
+    sched = O.window_schedule(240, 10, 10, 80)
+    eng = E.Engine.__new__(E.Engine)            # host-side method only: no device, no library call
+    per_slot = E.Engine.gen_slot_bytes(360, 640)
+    assert 20e6 < per_slot < 100e6
+    for budget_slots in (1000, 120, 40, 5):
+        parts = eng.gen_batches(sched, budget_slots * per_slot, (240, 360, 640))
+        assert [w for p in parts for w in p] == sched
+        for p in parts:
+            slots = sum(len(a) + len(b) for a, b in p)
+            assert slots <= budget_slots or len(p) == 1
+    assert len(eng.gen_batches(sched, 10 ** 15, (240, 360, 640))) == 1
+    # the per-clip arena estimate saturates for long clips and covers the measured peaks (24.3 GB at C2, 92 GB at C4)
+    assert E.Engine.clip_workspace_bytes(80, 360, 640) > 24.3e9 and E.Engine.clip_workspace_bytes(80, 720, 1280) > 92e9
+    assert E.Engine.clip_workspace_bytes(1000, 360, 640) == E.Engine.clip_workspace_bytes(100, 360, 640)
